@@ -1,0 +1,160 @@
+/*
+ * tealeaf_b200.h -- C-ABI of libtealeaf_b200.so, the B200-native (sm_100a) drop-in for the
+ * implicit heat-conduction solve of Laura7089/TeaLeaf.jl (CG / Chebyshev / PPCG on the
+ * 5-point stencil).
+ *
+ * The reference has no FFI (it is pure Julia); the entry points below are what a
+ * `ccall` binding placed under the reference's own function names would bind.  Each
+ * declaration cites the reference function it replaces (file:line under the reference
+ * tree).  julia/TeaLeafB200.jl holds that binding; INTEGRATION.md shows how it is wired
+ * into src/TeaLeaf.jl.
+ *
+ * Conventions
+ *  - plain C: pointers, ints, doubles; no C++/torch types cross the boundary.
+ *  - every function returns TL_OK (0) or a negative tl_status; the message is available
+ *    from tl_last_error(ctx) until the next call on that context.  Nothing throws.
+ *  - the library owns all device memory.  Host pointers are borrowed for the duration of
+ *    the call only.  Out-scalars are caller-owned and are valid when the call returns
+ *    (every call is synchronous with respect to its outputs).
+ *  - host field layout is the reference's: Julia column-major (x, y) Float64 including
+ *    halos, x = xcells + 2*halo_depth contiguous (src/chunk.jl:68-70); element [kk,jj]
+ *    (1-based) is host[(kk-1) + (jj-1)*ld].
+ *  - one caller thread per context (the reference is single-threaded).
+ *  - one context == one GPU == one tile of the px x py decomposition (one process per
+ *    GPU; see tl_comm_*).  A single-GPU run is the 1x1 case.
+ */
+#ifndef TEALEAF_B200_H
+#define TEALEAF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TL_ABI_VERSION 1
+
+typedef struct tl_ctx tl_ctx;
+
+typedef enum tl_status {
+  TL_OK = 0,
+  TL_ERR_ARG = -1,        /* invalid argument (e.g. coefficient not 1|2, src/solvers/CG.jl:48-50) */
+  TL_ERR_CUDA = -2,       /* a CUDA runtime call failed */
+  TL_ERR_NO_DEVICE = -3,  /* no usable sm_100 device: there is NO CPU fallback */
+  TL_ERR_EIGEN = -4,      /* eigenvalue estimate failed / negative (src/kernels.jl:41-43, :80) */
+  TL_ERR_COMM = -5,       /* NCCL / IPC failure */
+  TL_ERR_STATE = -6       /* call sequence error (e.g. comm not connected) */
+} tl_status;
+
+/* Chunk fields, src/chunk.jl:25-38.  (density0, mi are never read on the path.) */
+typedef enum tl_field {
+  TL_DENSITY = 0, TL_ENERGY0 = 1, TL_ENERGY = 2, TL_U = 3, TL_U0 = 4, TL_P = 5,
+  TL_R = 6, TL_W = 7, TL_KX = 8, TL_KY = 9, TL_SD = 10, TL_NUM_FIELDS = 11
+} tl_field;
+#define TL_MASK(f) (1u << (f))
+
+#define TL_CONDUCTIVITY 1        /* src/settings.jl:13 */
+#define TL_RECIP_CONDUCTIVITY 2  /* src/settings.jl:14 */
+
+/* Result of a whole solve (what the reference logs: CG.jl:27, Cheby.jl:60, PPCG.jl:54). */
+typedef struct tl_solve_info {
+  int iters;         /* outer iterations executed (`tt` at loop exit) */
+  int cg_iters;      /* CG iterations among them (all of them for CG; the presteps otherwise) */
+  int cheby_iters;   /* Chebyshev iterations (Cheby) or PPCG outer iterations (PPCG) */
+  int est_iters;     /* Cheby.calciter estimate (Cheby.jl:109-118) */
+  int inner_total;   /* PPCG inner steps executed */
+  int reserved;
+  double error;      /* final `error` (rr) */
+  double eigmin, eigmax;
+  double solve_ms;   /* device time of the solve, CUDA events on the solve stream */
+  long long kernel_launches;  /* kernels launched by this solve */
+} tl_solve_info;
+
+/* ---- context ------------------------------------------------------------------ */
+
+/* Chunk(settings), src/chunk.jl:68-89: allocates every field for an xcells x ycells tile
+ * with `halo_depth` halo cells per side on CUDA device `device`. */
+int tl_create(tl_ctx **out, int xcells, int ycells, int halo_depth, int max_iters, int device);
+/* Same, for tile `rank` (= cx + cy*px) of a px x py decomposition; sides that touch
+ * another tile are exchanged, the others are reflective (src/kernels.jl:191-210). */
+int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_depth, int max_iters, int device,
+                   int rank, int px, int py);
+void tl_destroy(tl_ctx *ctx);
+const char *tl_last_error(const tl_ctx *ctx);
+int tl_abi_version(void);
+/* tuning knob (name = "chunk_rows", "blocks_per_sm", "graph_iters", "l2_pin_mb", ...) */
+int tl_set_option(tl_ctx *ctx, const char *name, double value);
+
+/* ---- multi-GPU wiring (no counterpart in the reference: it has a single Chunk) ---- */
+int tl_comm_blob_size(void);                       /* bytes of one exported blob */
+int tl_comm_export(tl_ctx *ctx, void *blob);       /* CUDA-IPC handle + tile descriptor */
+int tl_comm_unique_id(void *id128);                /* ncclGetUniqueId (rank 0), 128 bytes */
+/* all_blobs: px*py blobs in rank order; id128: the broadcast NCCL id. */
+int tl_comm_connect(tl_ctx *ctx, const void *all_blobs, const void *id128);
+
+/* ---- field transfer (getfield/setfield of Chunk, src/chunk.jl:25-38) ---------- */
+int tl_set_field(tl_ctx *ctx, int field, const double *host, long ld);
+int tl_get_field(tl_ctx *ctx, int field, double *host, long ld);
+/* `chunk.dst .= chunk.src` on the whole array, device to device (src/TeaLeaf.jl:41) */
+int tl_copy_field(tl_ctx *ctx, int dst_field, int src_field);
+
+/* ---- kernels, one per reference function -------------------------------------- */
+/* haloupdate!/updateface!, src/kernels.jl:146-159, :191-210 (depth-`depth` faces of every
+ * field in field_mask; the sticky `toexchange` set stays on the Julia side). */
+int tl_halo_update(tl_ctx *ctx, unsigned field_mask, int depth);
+/* CG.init!, src/solvers/CG.jl:47-79 -> rro */
+int tl_cg_init(tl_ctx *ctx, int coefficient, double rx, double ry, double *rro);
+/* CG.w!, src/solvers/CG.jl:82-90 -> pw */
+int tl_cg_calc_w(tl_ctx *ctx, double *pw);
+/* CG.ur!, src/solvers/CG.jl:93-98 -> rrn */
+int tl_cg_calc_ur(tl_ctx *ctx, double alpha, double *rrn);
+/* CG.p!, src/solvers/CG.jl:101-104 */
+int tl_cg_calc_p(tl_ctx *ctx, double beta);
+/* copyu!, src/kernels.jl:217-220 */
+int tl_copy_u(tl_ctx *ctx);
+/* residual!, src/kernels.jl:227-232 */
+int tl_calc_residual(tl_ctx *ctx);
+/* finalise!, src/kernels.jl:239-242 */
+int tl_finalise(tl_ctx *ctx);
+/* solvefinished!, src/kernels.jl:166-170 (residual if check_result, finalise, halo energy) */
+int tl_solve_finished(tl_ctx *ctx, int check_result);
+/* sum(x->x^2, field[halo]) as used at Cheby.jl:68, :103 and PPCG.jl:88 */
+int tl_norm2(tl_ctx *ctx, int field, double *out);
+/* field part of Cheby.init!, src/solvers/Cheby.jl:64-81 (theta from coef!) -> bb */
+int tl_cheby_init(tl_ctx *ctx, double theta, double *bb);
+/* Cheby.mainstep!, src/solvers/Cheby.jl:84-106; alpha/beta = chebyα/β[chebyiters+1];
+ * *error is updated only when calc_2norm != 0. */
+int tl_cheby_iterate(tl_ctx *ctx, double alpha, double beta, int calc_2norm, double *error);
+/* PPCG.init!(chunk, hd), src/solvers/PPCG.jl:97-100: sd = r / theta */
+int tl_ppcg_init_sd(tl_ctx *ctx, double theta);
+/* the inner loop of PPCG.mainstep!, src/solvers/PPCG.jl:75-84: nsteps x
+ * { halo(sd); r -= A sd; u += sd; sd = alphas[pp] sd + betas[pp] r } (two-phase). */
+int tl_ppcg_inner(tl_ctx *ctx, const double *alphas, const double *betas, int nsteps);
+/* fieldsummary, src/kernels.jl:119-133: temp = sum(volume*density*u); vol, mass, ie are
+ * the upstream companions named by the parity criterion. */
+int tl_field_summary(tl_ctx *ctx, double cell_volume, double *vol, double *mass, double *ie, double *temp);
+
+/* ---- whole-solve fast paths: `settings.solver.solve!(chunk, settings, rx, ry)`,
+ *      src/TeaLeaf.jl:74.  Fused kernels, device-resident scalars, graph-launched. ---- */
+/* CG.solve!, src/solvers/CG.jl:7-29.  cg_alphas/cg_betas (nullable) receive chunk.cgα/cgβ. */
+int tl_cg_solve(tl_ctx *ctx, int coefficient, double rx, double ry, double eps, int max_iters,
+                tl_solve_info *info, double *cg_alphas, double *cg_betas);
+/* Cheby.solve!, src/solvers/Cheby.jl:10-61 */
+int tl_cheby_solve(tl_ctx *ctx, int coefficient, double rx, double ry, double eps, int max_iters,
+                   int presteps, double epslim, int errorswitch, tl_solve_info *info);
+/* PPCG.solve!, src/solvers/PPCG.jl:9-55 */
+int tl_ppcg_solve(tl_ctx *ctx, int coefficient, double rx, double ry, double eps, int max_iters,
+                  int presteps, double epslim, int errorswitch, int inner_steps, tl_solve_info *info);
+
+/* ---- measurement helpers (bench.py) -------------------------------------------- */
+/* average device time (ms) of the named fused kernel over `reps` launches on the current
+ * state, CUDA events on the launch stream; fields are left modified. */
+int tl_time_kernel(tl_ctx *ctx, const char *kernel, int reps, double *avg_ms);
+/* CUDA-event stopwatch on the context's stream (the stream every kernel is launched on). */
+int tl_timer_start(tl_ctx *ctx);
+int tl_timer_stop(tl_ctx *ctx, double *elapsed_ms);
+/* kernels launched by this context so far (graph-launched kernels included) */
+int tl_launch_count(tl_ctx *ctx, long long *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEALEAF_B200_H */

@@ -1,0 +1,1071 @@
+// tl_api.cu -- context, C-ABI entry points (include/tealeaf_b200.h) and the whole-solve
+// drivers of libtealeaf_b200.so.  Built for sm_100a only; there is no CPU fallback: every
+// entry point fails with TL_ERR_NO_DEVICE / TL_ERR_CUDA when no usable GPU is present.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <climits>
+#include <string>
+#include <vector>
+#include <algorithm>
+#ifdef TL_WITH_NCCL
+#include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
+#include <dlfcn.h>
+#endif
+
+#include "../../include/tealeaf_b200.h"
+#include "tl_device.cuh"
+#include "tl_kernels_basic.cuh"
+#include "tl_kernels_fused.cuh"
+#include "tl_eigen.h"
+
+#define TL_MAX_GRID 4096
+#define TL_ERROR_START 1e10       // src/kernels.jl:7
+#define TL_ERROR_SWITCH_MAX 1.0   // src/kernels.jl:8
+#define TL_CGEIGENITERS 20        // src/solvers/Cheby.jl:7
+
+enum { B_P1 = TL_NUM_FIELDS, B_U1, B_SD1, B_COUNT };  // ping-pong partners of p, u, sd
+
+#ifdef TL_WITH_NCCL
+// NCCL is bound lazily with dlopen instead of at link time: a process that also imports torch
+// must end up with ONE libnccl.so.2 (torch bundles a newer one than the system's), so an
+// already-loaded copy is preferred (RTLD_NOLOAD) and the system copy is the fallback.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi &nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+  return api;
+}
+#endif
+
+struct CommBlob {  // what tl_comm_export hands to the other ranks
+  cudaIpcMemHandle_t handle;
+  int nx, ny, hd, pitch;
+  long long buf_offset[B_COUNT];  // byte offset of interior cell (0,0) of each buffer in the slab
+  int rank, device;
+};
+
+struct tl_ctx {
+  Geo g{};
+  int max_iters = 0, device = 0;
+  int rank = 0, px = 1, py = 1, cx = 0, cy = 0, nranks = 1;
+  size_t rows = 0, buf_doubles = 0;
+  char *slab = nullptr;
+  size_t slab_bytes = 0;
+  double *buf[B_COUNT]{};   // interior-origin pointers
+  int p_cur = 0, u_cur = 0, sd_cur = 0;
+  SolveState *st = nullptr;
+  double *hist_rr = nullptr, *hist_pw = nullptr, *ch_alphas = nullptr, *ch_betas = nullptr, *partials = nullptr;
+  SolveState *h_st = nullptr;   // pinned, 2 polling slots
+  double *h_scal = nullptr;     // pinned scratch
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2]{}, ev_start = nullptr, ev_stop = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  int num_sms = 148;
+  // tuning
+  int blocks_per_sm = 2, chunk_rows = 0, graph_iters = 8, use_graph = 1;
+  Tiling tiling{};
+  int fused_grid = 0, basic_grid = 0;
+  cudaGraphExec_t g_cg = nullptr, g_cheby = nullptr, g_ppcg = nullptr;
+  int g_cg_iters = 0, g_cheby_iters = 0, g_ppcg_iters = 0, g_ppcg_inner = 0;
+  long long launches = 0;
+  // peers (tile-internal sides): 0 left, 1 right, 2 bottom, 3 top
+  int nbr_rank[4] = {-1, -1, -1, -1};
+  void *peer_slab[4]{};
+  CommBlob peer_blob[4]{};
+  bool comm_ready = false;
+#ifdef TL_WITH_NCCL
+  ncclComm_t nccl = nullptr;
+#endif
+  std::string err;
+};
+
+static int tl_fail(tl_ctx *c, int code, const char *fmt, ...) {
+  char b[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(b, sizeof b, fmt, ap); va_end(ap);
+  if (c) c->err = b;
+  return code;
+}
+#define CU(c, call)                                                                               \
+  do { cudaError_t _e = (call);                                                                   \
+       if (_e != cudaSuccess) return tl_fail((c), TL_ERR_CUDA, "%s failed: %s (%s:%d)", #call,    \
+                                             cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
+#define CHECK_LAUNCH(c) CU(c, cudaGetLastError())
+#define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+static double *field_ptr(tl_ctx *c, int f) {
+  if (f == TL_P) return c->buf[c->p_cur ? B_P1 : TL_P];
+  if (f == TL_U) return c->buf[c->u_cur ? B_U1 : TL_U];
+  if (f == TL_SD) return c->buf[c->sd_cur ? B_SD1 : TL_SD];
+  return c->buf[f];
+}
+
+static void compute_tiling(tl_ctx *c) {
+  const Geo &g = c->g;
+  Tiling t;
+  t.nstrips = (g.nx + TL_STRIP - 1) / TL_STRIP;
+  const int wpb = TL_FUSED_THREADS / 32;
+  const int target_warps = c->num_sms * c->blocks_per_sm * wpb;
+  int nchunks = std::max(1, target_warps / t.nstrips);
+  if (c->chunk_rows > 0) nchunks = (g.ny + c->chunk_rows - 1) / c->chunk_rows;
+  nchunks = std::min(nchunks, g.ny);
+  t.rows_per_chunk = (g.ny + nchunks - 1) / nchunks;
+  t.nchunks = (g.ny + t.rows_per_chunk - 1) / t.rows_per_chunk;
+  c->tiling = t;
+  c->fused_grid = (t.nstrips * t.nchunks + wpb - 1) / wpb;
+  if (c->fused_grid > TL_MAX_GRID) {  // keep the partials array bounded
+    const int max_warps = TL_MAX_GRID * wpb;
+    nchunks = std::max(1, max_warps / t.nstrips);
+    t.rows_per_chunk = (g.ny + nchunks - 1) / nchunks;
+    t.nchunks = (g.ny + t.rows_per_chunk - 1) / t.rows_per_chunk;
+    c->tiling = t;
+    c->fused_grid = (t.nstrips * t.nchunks + wpb - 1) / wpb;
+  }
+  const long cells = (long)(g.nx + 2 * g.hd) * (g.ny + 2 * g.hd);
+  long nb = (cells + TL_BASIC_THREADS - 1) / TL_BASIC_THREADS;
+  c->basic_grid = (int)std::max(1L, std::min<long>(nb, (long)c->num_sms * 8));
+}
+
+static void destroy_graphs(tl_ctx *c) {
+  if (c->g_cg) { cudaGraphExecDestroy(c->g_cg); c->g_cg = nullptr; }
+  if (c->g_cheby) { cudaGraphExecDestroy(c->g_cheby); c->g_cheby = nullptr; }
+  if (c->g_ppcg) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
+}
+
+extern "C" int tl_abi_version(void) { return TL_ABI_VERSION; }
+
+extern "C" const char *tl_last_error(const tl_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+static std::string g_create_error;
+
+extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_depth, int max_iters, int device,
+                              int rank, int px, int py) {
+  if (!out) return TL_ERR_ARG;
+  *out = nullptr;
+  if (xcells < 1 || ycells < 1 || halo_depth < 1 || halo_depth > TL_XPAD || max_iters < 1 || px < 1 || py < 1 ||
+      rank < 0 || rank >= px * py)
+    return TL_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device >= ndev) {
+    cudaGetLastError();
+    return TL_ERR_NO_DEVICE;
+  }
+  tl_ctx *c = new tl_ctx();
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return TL_ERR_NO_DEVICE; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+    delete c;
+    return TL_ERR_NO_DEVICE;  // sm_100a-only binary
+  }
+  c->num_sms = prop.multiProcessorCount;
+  c->max_iters = max_iters;
+  c->rank = rank; c->px = px; c->py = py; c->cx = rank % px; c->cy = rank / px; c->nranks = px * py;
+  Geo &g = c->g;
+  g.nx = xcells; g.ny = ycells; g.hd = halo_depth;
+  g.pitch = TL_XPAD + ((xcells + halo_depth + 2 + 15) / 16) * 16;
+  g.phys = 0;
+  if (c->cx == 0) g.phys |= TL_PHYS_LEFT; else c->nbr_rank[0] = rank - 1;
+  if (c->cx == px - 1) g.phys |= TL_PHYS_RIGHT; else c->nbr_rank[1] = rank + 1;
+  if (c->cy == 0) g.phys |= TL_PHYS_BOTTOM; else c->nbr_rank[2] = rank - px;
+  if (c->cy == py - 1) g.phys |= TL_PHYS_TOP; else c->nbr_rank[3] = rank + px;
+  c->rows = (size_t)ycells + 2 * halo_depth;
+  c->buf_doubles = ((c->rows * g.pitch + 31) / 32) * 32;
+
+  const size_t hist = ((size_t)max_iters + 8 + 31) / 32 * 32;
+  size_t bytes = (size_t)B_COUNT * c->buf_doubles * sizeof(double);
+  const size_t off_state = bytes; bytes += 4096;
+  const size_t off_hist = bytes; bytes += 4 * hist * sizeof(double);
+  const size_t off_part = bytes; bytes += 4 * TL_MAX_GRID * sizeof(double);
+  c->slab_bytes = bytes;
+  cudaError_t e = cudaMalloc((void **)&c->slab, bytes);
+  if (e != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete c;
+    return TL_ERR_CUDA;
+  }
+  cudaMemset(c->slab, 0, bytes);
+  for (int b = 0; b < B_COUNT; b++)
+    c->buf[b] = (double *)c->slab + (size_t)b * c->buf_doubles + (size_t)halo_depth * g.pitch + TL_XPAD;
+  c->st = (SolveState *)(c->slab + off_state);
+  c->hist_rr = (double *)(c->slab + off_hist);
+  c->hist_pw = c->hist_rr + hist;
+  c->ch_alphas = c->hist_pw + hist;
+  c->ch_betas = c->ch_alphas + hist;
+  c->partials = (double *)(c->slab + off_part);
+  if (cudaMallocHost((void **)&c->h_st, 2 * sizeof(SolveState)) != cudaSuccess ||
+      cudaMallocHost((void **)&c->h_scal, 64 * sizeof(double)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||
+      cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(cudaGetLastError());
+    tl_destroy(c);
+    return TL_ERR_CUDA;
+  }
+  compute_tiling(c);
+  cudaDeviceSynchronize();
+  *out = c;
+  return TL_OK;
+}
+
+extern "C" int tl_create(tl_ctx **out, int xcells, int ycells, int halo_depth, int max_iters, int device) {
+  return tl_create_tile(out, xcells, ycells, halo_depth, max_iters, device, 0, 1, 1);
+}
+
+extern "C" void tl_destroy(tl_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  destroy_graphs(c);
+#ifdef TL_WITH_NCCL
+  if (c->nccl && nccl_api().ok) nccl_api().CommDestroy(c->nccl);
+#endif
+  for (int s = 0; s < 4; s++)
+    if (c->peer_slab[s]) cudaIpcCloseMemHandle(c->peer_slab[s]);
+  if (c->ev[0]) cudaEventDestroy(c->ev[0]);
+  if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
+  if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->h_st) cudaFreeHost(c->h_st);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  if (c->slab) cudaFree(c->slab);
+  delete c;
+}
+
+extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
+  if (!c || !name) return TL_ERR_ARG;
+  const std::string n(name);
+  if (n == "blocks_per_sm") c->blocks_per_sm = std::max(1, (int)value);
+  else if (n == "chunk_rows") c->chunk_rows = std::max(0, (int)value);
+  else if (n == "graph_iters") c->graph_iters = std::max(1, (int)value);
+  else if (n == "use_graph") c->use_graph = value != 0.0;
+  else return tl_fail(c, TL_ERR_ARG, "unknown option %s", name);
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  destroy_graphs(c);
+  compute_tiling(c);
+  return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU wiring
+// ---------------------------------------------------------------------------------------
+extern "C" int tl_comm_blob_size(void) { return (int)sizeof(CommBlob); }
+
+extern "C" int tl_comm_export(tl_ctx *c, void *blob) {
+  if (!c || !blob) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CommBlob b;
+  memset(&b, 0, sizeof b);
+  CU(c, cudaIpcGetMemHandle(&b.handle, c->slab));
+  b.nx = c->g.nx; b.ny = c->g.ny; b.hd = c->g.hd; b.pitch = c->g.pitch;
+  for (int i = 0; i < B_COUNT; i++) b.buf_offset[i] = (long long)((char *)c->buf[i] - c->slab);
+  b.rank = c->rank; b.device = c->device;
+  memcpy(blob, &b, sizeof b);
+  return TL_OK;
+}
+
+extern "C" int tl_comm_unique_id(void *id128) {
+#ifdef TL_WITH_NCCL
+  ncclUniqueId id;
+  if (!nccl_api().ok || nccl_api().GetUniqueId(&id) != ncclSuccess) return TL_ERR_COMM;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(id128, &id, 128);
+  return TL_OK;
+#else
+  (void)id128;
+  return TL_ERR_COMM;
+#endif
+}
+
+extern "C" int tl_comm_connect(tl_ctx *c, const void *all_blobs, const void *id128) {
+  if (!c) return TL_ERR_ARG;
+  if (c->nranks == 1) { c->comm_ready = true; return TL_OK; }
+  if (!all_blobs || !id128) return tl_fail(c, TL_ERR_ARG, "tl_comm_connect: blobs and NCCL id are required");
+  CU(c, cudaSetDevice(c->device));
+  const CommBlob *blobs = (const CommBlob *)all_blobs;
+  for (int s = 0; s < 4; s++) {
+    const int nr = c->nbr_rank[s];
+    if (nr < 0) continue;
+    c->peer_blob[s] = blobs[nr];
+    CU(c, cudaIpcOpenMemHandle(&c->peer_slab[s], blobs[nr].handle, cudaIpcMemLazyEnablePeerAccess));
+  }
+#ifdef TL_WITH_NCCL
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  if (!nccl_api().ok) return tl_fail(c, TL_ERR_COMM, "libnccl.so.2 could not be loaded");
+  ncclResult_t r = nccl_api().CommInitRank(&c->nccl, c->nranks, id, c->rank);
+  if (r != ncclSuccess) return tl_fail(c, TL_ERR_COMM, "ncclCommInitRank: %s", nccl_api().GetErrorString(r));
+#else
+  return tl_fail(c, TL_ERR_COMM, "library built without NCCL");
+#endif
+  c->comm_ready = true;
+  return TL_OK;
+}
+
+// sum over tiles of n doubles living in device memory (stream ordered)
+static int allreduce(tl_ctx *c, double *dev, int n) {
+  if (c->nranks == 1) return TL_OK;
+  if (!c->comm_ready) return tl_fail(c, TL_ERR_STATE, "tile context used before tl_comm_connect");
+#ifdef TL_WITH_NCCL
+  ncclResult_t r = nccl_api().AllReduce(dev, dev, n, ncclDouble, ncclSum, c->nccl, c->stream);
+  if (r != ncclSuccess) return tl_fail(c, TL_ERR_COMM, "ncclAllReduce: %s", nccl_api().GetErrorString(r));
+  return TL_OK;
+#else
+  return tl_fail(c, TL_ERR_COMM, "library built without NCCL");
+#endif
+}
+
+static PeerFace peer_face(tl_ctx *c, int side, int bufidx) {
+  PeerFace f{nullptr, 0, 0, 0};
+  if (c->nbr_rank[side] < 0 || !c->peer_slab[side]) return f;
+  const CommBlob &b = c->peer_blob[side];
+  f.f0 = (const double *)((char *)c->peer_slab[side] + b.buf_offset[bufidx]);
+  f.nx = b.nx; f.ny = b.ny; f.pitch = b.pitch;
+  return f;
+}
+
+static int buf_index(tl_ctx *c, int f) {
+  if (f == TL_P) return c->p_cur ? B_P1 : TL_P;
+  if (f == TL_U) return c->u_cur ? B_U1 : TL_U;
+  if (f == TL_SD) return c->sd_cur ? B_SD1 : TL_SD;
+  return f;
+}
+
+// tile-internal halos of buffer `bufidx`; the caller guarantees (through a preceding
+// allreduce or tl_comm barrier) that the neighbours have finished writing it.
+static int pull_halo(tl_ctx *c, int bufidx, int depth) {
+  if (c->nranks == 1) return TL_OK;
+  const int total = 2 * depth * (c->g.nx + c->g.ny);
+  const int grid = std::min((total + 255) / 256, c->num_sms * 4);
+  k_pull_halo<<<grid, 256, 0, c->stream>>>(c->g, depth, c->buf[bufidx], peer_face(c, 0, bufidx),
+                                           peer_face(c, 1, bufidx), peer_face(c, 2, bufidx), peer_face(c, 3, bufidx));
+  c->launches++;
+  CHECK_LAUNCH(c);
+  return TL_OK;
+}
+
+// a device-side rendezvous of all tiles (1-double allreduce); used where a halo pull is not
+// already ordered by a dot-product allreduce.
+static int tile_barrier(tl_ctx *c) {
+  if (c->nranks == 1) return TL_OK;
+  return allreduce(c, &c->st->red_aux[3], 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// field transfer
+// ---------------------------------------------------------------------------------------
+extern "C" int tl_set_field(tl_ctx *c, int field, const double *host, long ld) {
+  if (!c || !host || field < 0 || field >= TL_NUM_FIELDS) return tl_fail(c, TL_ERR_ARG, "tl_set_field: bad argument");
+  const Geo &g = c->g;
+  const int x = g.nx + 2 * g.hd, y = g.ny + 2 * g.hd;
+  if (ld < x) return tl_fail(c, TL_ERR_ARG, "tl_set_field: ld < x");
+  CU(c, cudaSetDevice(c->device));
+  double *dst = field_ptr(c, field) - (long)g.hd * g.pitch - g.hd;
+  CU(c, cudaMemcpy2DAsync(dst, (size_t)g.pitch * 8, host, (size_t)ld * 8, (size_t)x * 8, y, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+extern "C" int tl_get_field(tl_ctx *c, int field, double *host, long ld) {
+  if (!c || !host || field < 0 || field >= TL_NUM_FIELDS) return tl_fail(c, TL_ERR_ARG, "tl_get_field: bad argument");
+  const Geo &g = c->g;
+  const int x = g.nx + 2 * g.hd, y = g.ny + 2 * g.hd;
+  if (ld < x) return tl_fail(c, TL_ERR_ARG, "tl_get_field: ld < x");
+  CU(c, cudaSetDevice(c->device));
+  const double *src = field_ptr(c, field) - (long)g.hd * g.pitch - g.hd;
+  CU(c, cudaMemcpy2DAsync(host, (size_t)ld * 8, src, (size_t)g.pitch * 8, (size_t)x * 8, y, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+extern "C" int tl_copy_field(tl_ctx *c, int dst_field, int src_field) {
+  if (!c || dst_field < 0 || dst_field >= TL_NUM_FIELDS || src_field < 0 || src_field >= TL_NUM_FIELDS)
+    return tl_fail(c, TL_ERR_ARG, "tl_copy_field: bad field");
+  CU(c, cudaSetDevice(c->device));
+  const Geo &g = c->g;
+  const size_t off = (size_t)g.hd * g.pitch + TL_XPAD;
+  CU(c, cudaMemcpyAsync(field_ptr(c, dst_field) - off, field_ptr(c, src_field) - off,
+                        c->rows * g.pitch * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-function kernels
+// ---------------------------------------------------------------------------------------
+#define LAUNCH_BASIC(c, kern, ...)                                                      \
+  do { kern<<<(c)->basic_grid, TL_BASIC_THREADS, 0, (c)->stream>>>(__VA_ARGS__);        \
+       (c)->launches++; CHECK_LAUNCH(c); } while (0)
+
+static int read_scalars(tl_ctx *c, const double *dev, int n, double *out) {
+  CU(c, cudaMemcpyAsync(c->h_scal, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; i++) out[i] = c->h_scal[i];
+  return TL_OK;
+}
+
+static int halo_update_buf(tl_ctx *c, int bufidx, int depth) {
+  const int total = 2 * depth * (c->g.nx + c->g.ny);
+  const int grid = std::min((total + 255) / 256, c->num_sms * 4);
+  if (c->g.phys) {
+    k_halo_reflect<<<grid, 256, 0, c->stream>>>(c->g, depth, c->buf[bufidx]);
+    c->launches++;
+    CHECK_LAUNCH(c);
+  }
+  return pull_halo(c, bufidx, depth);
+}
+
+extern "C" int tl_halo_update(tl_ctx *c, unsigned field_mask, int depth) {
+  if (!c || depth < 1 || depth > c->g.hd) return tl_fail(c, TL_ERR_ARG, "tl_halo_update: depth must be in 1..halo_depth");
+  CU(c, cudaSetDevice(c->device));
+  TRY(tile_barrier(c));  // neighbours' interiors must be final before they are pulled
+  for (int f = 0; f < TL_NUM_FIELDS; f++)
+    if (field_mask & (1u << f)) TRY(halo_update_buf(c, buf_index(c, f), depth));
+  TRY(tile_barrier(c));  // nobody overwrites an interior a neighbour is still reading
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+// CG.init! (CG.jl:47-79), asynchronous part: leaves rro in st->red_rr (all-reduced).
+static int cg_init_async(tl_ctx *c, int coef, double rx, double ry) {
+  if (coef != TL_CONDUCTIVITY && coef != TL_RECIP_CONDUCTIVITY)
+    return tl_fail(c, TL_ERR_ARG, "Coefficient %d is not valid", coef);  // CG.jl:48-50
+  c->p_cur = c->u_cur = c->sd_cur = 0;
+  const Geo &g = c->g;
+  LAUNCH_BASIC(c, k_init_fields, g, coef, c->buf[TL_ENERGY], c->buf[TL_DENSITY], c->buf[TL_U], c->buf[TL_P],
+               c->buf[TL_R], c->buf[TL_W]);
+  LAUNCH_BASIC(c, k_init_k, g, rx, ry, c->buf[TL_W], c->buf[TL_KX], c->buf[TL_KY]);
+  LAUNCH_BASIC(c, k_init_wrp, g, c->buf[TL_U], c->buf[TL_KX], c->buf[TL_KY], c->buf[TL_W], c->buf[TL_R],
+               c->buf[TL_P], c->partials, &c->st->counter, &c->st->red_rr);
+  return allreduce(c, &c->st->red_rr, 1);
+}
+
+extern "C" int tl_cg_init(tl_ctx *c, int coef, double rx, double ry, double *rro) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  TRY(cg_init_async(c, coef, rx, ry));
+  double v;
+  TRY(read_scalars(c, &c->st->red_rr, 1, &v));
+  if (rro) *rro = v;
+  return TL_OK;
+}
+
+extern "C" int tl_cg_calc_w(tl_ctx *c, double *pw) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  LAUNCH_BASIC(c, k_calc_w, c->g, field_ptr(c, TL_P), c->buf[TL_KX], c->buf[TL_KY], c->buf[TL_W], c->partials,
+               &c->st->counter, &c->st->red_pw);
+  TRY(allreduce(c, &c->st->red_pw, 1));
+  double v;
+  TRY(read_scalars(c, &c->st->red_pw, 1, &v));
+  if (pw) *pw = v;
+  return TL_OK;
+}
+
+extern "C" int tl_cg_calc_ur(tl_ctx *c, double alpha, double *rrn) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  LAUNCH_BASIC(c, k_calc_ur, c->g, alpha, field_ptr(c, TL_P), c->buf[TL_W], field_ptr(c, TL_U), c->buf[TL_R],
+               c->partials, &c->st->counter, &c->st->red_aux[0]);
+  TRY(allreduce(c, &c->st->red_aux[0], 1));
+  double v;
+  TRY(read_scalars(c, &c->st->red_aux[0], 1, &v));
+  if (rrn) *rrn = v;
+  return TL_OK;
+}
+
+extern "C" int tl_cg_calc_p(tl_ctx *c, double beta) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  LAUNCH_BASIC(c, k_calc_p, c->g, beta, c->buf[TL_R], field_ptr(c, TL_P));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+extern "C" int tl_copy_u(tl_ctx *c) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  LAUNCH_BASIC(c, k_copy, c->g, 0, field_ptr(c, TL_U), c->buf[TL_U0]);
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+static int residual_async(tl_ctx *c) {
+  LAUNCH_BASIC(c, k_residual, c->g, field_ptr(c, TL_U), c->buf[TL_U0], c->buf[TL_KX], c->buf[TL_KY], c->buf[TL_R]);
+  return TL_OK;
+}
+extern "C" int tl_calc_residual(tl_ctx *c) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  TRY(residual_async(c));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+extern "C" int tl_finalise(tl_ctx *c) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  LAUNCH_BASIC(c, k_finalise, c->g, field_ptr(c, TL_U), c->buf[TL_DENSITY], c->buf[TL_ENERGY]);
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+extern "C" int tl_solve_finished(tl_ctx *c, int check_result) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  if (check_result) TRY(residual_async(c));
+  LAUNCH_BASIC(c, k_finalise, c->g, field_ptr(c, TL_U), c->buf[TL_DENSITY], c->buf[TL_ENERGY]);
+  CU(c, cudaStreamSynchronize(c->stream));
+  return tl_halo_update(c, TL_MASK(TL_ENERGY), 1);
+}
+
+static int norm2_async(tl_ctx *c, int field, double *dev_out) {
+  LAUNCH_BASIC(c, k_norm2, c->g, field_ptr(c, field), c->partials, &c->st->counter, dev_out);
+  return allreduce(c, dev_out, 1);
+}
+extern "C" int tl_norm2(tl_ctx *c, int field, double *out) {
+  if (!c || field < 0 || field >= TL_NUM_FIELDS) return tl_fail(c, TL_ERR_ARG, "tl_norm2: bad field");
+  CU(c, cudaSetDevice(c->device));
+  TRY(norm2_async(c, field, &c->st->red_aux[0]));
+  double v;
+  TRY(read_scalars(c, &c->st->red_aux[0], 1, &v));
+  if (out) *out = v;
+  return TL_OK;
+}
+
+extern "C" int tl_cheby_init(tl_ctx *c, double theta, double *bb) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  TRY(norm2_async(c, TL_U0, &c->st->red_aux[0]));   // Cheby.jl:68
+  LAUNCH_BASIC(c, k_cheby_wrp, c->g, 1, theta, 0.0, 0.0, field_ptr(c, TL_U), c->buf[TL_U0], c->buf[TL_KX],
+               c->buf[TL_KY], c->buf[TL_W], c->buf[TL_R], field_ptr(c, TL_P));
+  LAUNCH_BASIC(c, k_add, c->g, field_ptr(c, TL_P), field_ptr(c, TL_U));
+  double v;
+  TRY(read_scalars(c, &c->st->red_aux[0], 1, &v));
+  if (bb) *bb = v;
+  return tl_halo_update(c, TL_MASK(TL_U), 1);        // Cheby.jl:78
+}
+
+extern "C" int tl_cheby_iterate(tl_ctx *c, double alpha, double beta, int calc_2norm, double *error) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  LAUNCH_BASIC(c, k_cheby_wrp, c->g, 0, 1.0, alpha, beta, field_ptr(c, TL_U), c->buf[TL_U0], c->buf[TL_KX],
+               c->buf[TL_KY], c->buf[TL_W], c->buf[TL_R], field_ptr(c, TL_P));
+  LAUNCH_BASIC(c, k_add, c->g, field_ptr(c, TL_P), field_ptr(c, TL_U));
+  if (calc_2norm) {
+    TRY(norm2_async(c, TL_R, &c->st->red_aux[0]));
+    double v;
+    TRY(read_scalars(c, &c->st->red_aux[0], 1, &v));
+    if (error) *error = v;
+  } else {
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  return TL_OK;
+}
+
+extern "C" int tl_ppcg_init_sd(tl_ctx *c, double theta) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  LAUNCH_BASIC(c, k_ppcg_init_sd, c->g, theta, c->buf[TL_R], field_ptr(c, TL_SD));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+extern "C" int tl_ppcg_inner(tl_ctx *c, const double *alphas, const double *betas, int nsteps) {
+  if (!c || !alphas || !betas || nsteps < 0) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_inner: bad argument");
+  CU(c, cudaSetDevice(c->device));
+  for (int pp = 0; pp < nsteps; pp++) {
+    TRY(tl_halo_update(c, TL_MASK(TL_SD), 1));   // PPCG.jl:76
+    LAUNCH_BASIC(c, k_ppcg_inner1, c->g, field_ptr(c, TL_SD), c->buf[TL_KX], c->buf[TL_KY], c->buf[TL_R], field_ptr(c, TL_U));
+    LAUNCH_BASIC(c, k_ppcg_inner2, c->g, alphas[pp], betas[pp], c->buf[TL_R], field_ptr(c, TL_SD));
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+extern "C" int tl_field_summary(tl_ctx *c, double cell_volume, double *vol, double *mass, double *ie, double *temp) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  LAUNCH_BASIC(c, k_field_summary, c->g, cell_volume, c->buf[TL_DENSITY], c->buf[TL_ENERGY0], field_ptr(c, TL_U),
+               c->partials, &c->st->counter, c->st->red_aux);
+  TRY(allreduce(c, c->st->red_aux, 4));
+  double v[4];
+  TRY(read_scalars(c, c->st->red_aux, 4, v));
+  if (vol) *vol = v[0];
+  if (mass) *mass = v[1];
+  if (ie) *ie = v[2];
+  if (temp) *temp = v[3];
+  return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// whole-solve drivers
+// ---------------------------------------------------------------------------------------
+__global__ void k_state_begin(SolveState *st, StopCfg cfg, int iter, double theta, int inner_steps) {
+  st->cfg = cfg;
+  st->iter = iter;
+  st->counter = 0u;
+  st->theta = theta;
+  st->inner_steps = inner_steps;
+  st->inner_pp = 0;
+}
+__global__ void k_state_cheby(SolveState *st, double theta, double eps, int tt0, int max_tt) {
+  st->theta = theta;
+  st->eps_cheby = eps;
+  st->cheby_step = 0;
+  st->cheby_done = 0;
+  st->cheby_est = INT_MAX;
+  st->cheby_tt0 = tt0;
+  st->cheby_max_tt = max_tt;
+  st->counter = 0u;
+}
+__global__ void k_state_set_est(SolveState *st, int est) { st->cheby_est = est; }
+
+static CgAParams cg_a_params(tl_ctx *c) {
+  CgAParams P;
+  P.g = c->g; P.t = c->tiling; P.st = c->st; P.hist_rr = c->hist_rr; P.hist_pw = c->hist_pw;
+  P.r = c->buf[TL_R]; P.p0 = c->buf[TL_P]; P.p1 = c->buf[B_P1]; P.u = c->buf[TL_U];
+  P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.w = c->buf[TL_W]; P.partials = c->partials;
+  return P;
+}
+static CgBParams cg_b_params(tl_ctx *c) {
+  CgBParams P;
+  P.g = c->g; P.t = c->tiling; P.st = c->st; P.hist_pw = c->hist_pw;
+  P.r = c->buf[TL_R]; P.w = c->buf[TL_W]; P.partials = c->partials;
+  return P;
+}
+
+// One CG iteration on the stream: [halo pulls of r, p when tiled] A, allreduce(pw), B, allreduce(rr).
+static int enqueue_cg_iteration(tl_ctx *c) {
+  if (c->nranks > 1) {
+    // r is final everywhere after the previous allreduce(rr); p_old after the one before.
+    TRY(pull_halo(c, TL_R, 1));
+    TRY(pull_halo(c, TL_P, 1));
+    TRY(pull_halo(c, B_P1, 1));
+  }
+  k_cg_fused_w<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
+  CHECK_LAUNCH(c);
+  TRY(allreduce(c, &c->st->red_pw, 1));
+  k_cg_fused_r<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
+  CHECK_LAUNCH(c);
+  TRY(allreduce(c, &c->st->red_rr, 1));
+  c->launches += 2;
+  return TL_OK;
+}
+
+template <typename F>
+static int build_graph(tl_ctx *c, cudaGraphExec_t *exec, int reps, F enqueue_one) {
+  cudaGraph_t graph = nullptr;
+  CU(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = TL_OK;
+  const long long saved = c->launches;
+  for (int i = 0; i < reps && rc == TL_OK; i++) rc = enqueue_one();
+  c->launches = saved;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) return tl_fail(c, TL_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return tl_fail(c, TL_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  return TL_OK;
+}
+
+// Runs chunks of `chunk_iters` iterations ahead of the host; `stopped(state)` is the host's
+// copy of the device-side stop rule.  On return the stream is idle and *final holds the state.
+template <typename Enq, typename Stop>
+static int run_chunks(tl_ctx *c, cudaGraphExec_t *exec, int *exec_iters, int chunk_iters, long long launches_per_iter,
+                      Enq enqueue_one, Stop stopped, SolveState *final_state) {
+  if (c->use_graph && (!*exec || *exec_iters != chunk_iters)) {
+    if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
+    TRY(build_graph(c, exec, chunk_iters, enqueue_one));
+    *exec_iters = chunk_iters;
+  }
+  int k = 0;
+  for (;; k++) {
+    if (c->use_graph) {
+      CU(c, cudaGraphLaunch(*exec, c->stream));
+      c->launches += launches_per_iter * chunk_iters;
+    } else {
+      for (int i = 0; i < chunk_iters; i++) TRY(enqueue_one());
+    }
+    CU(c, cudaMemcpyAsync(&c->h_st[k & 1], c->st, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaEventRecord(c->ev[k & 1], c->stream));
+    if (k >= 1) {
+      CU(c, cudaEventSynchronize(c->ev[(k - 1) & 1]));
+      if (stopped(c->h_st[(k - 1) & 1])) break;
+    }
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  *final_state = c->h_st[k & 1];
+  if (!stopped(*final_state)) return tl_fail(c, TL_ERR_STATE, "internal: chunk loop ended before the stop rule fired");
+  return TL_OK;
+}
+
+// CG preamble shared by the three solvers: CG.init!, haloupdate!([:u,:p]), copyu!  (CG.jl:9-12;
+// SURVEY Appendix A #12 for Cheby/PPCG)
+static int solve_preamble(tl_ctx *c, int coef, double rx, double ry, const StopCfg &cfg) {
+  TRY(cg_init_async(c, coef, rx, ry));
+  k_state_begin<<<1, 1, 0, c->stream>>>(c->st, cfg, 0, 0.0, 0);
+  c->launches++;
+  CHECK_LAUNCH(c);
+  if (c->nranks > 1) TRY(tile_barrier(c));
+  TRY(halo_update_buf(c, TL_U, 1));
+  TRY(halo_update_buf(c, TL_P, 1));
+  LAUNCH_BASIC(c, k_copy, c->g, 0, c->buf[TL_U], c->buf[TL_U0]);
+  return TL_OK;
+}
+
+static int cg_phase(tl_ctx *c, SolveState *fin) {
+  auto enq = [&]() { return enqueue_cg_iteration(c); };
+  auto stop = [&](const SolveState &s) { return tl_should_stop(s.iter, s.red_rr, s.cfg); };
+  return run_chunks(c, &c->g_cg, &c->g_cg_iters, c->graph_iters, 2, enq, stop, fin);
+}
+
+// flush the deferred p/u update of the last iteration and make buffer 0 the current p
+static int cg_flush(tl_ctx *c, int iters_done, bool update_u) {
+  if (update_u) k_cg_flush<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
+  else k_cg_flush<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
+  c->launches++;
+  CHECK_LAUNCH(c);
+  c->p_cur = iters_done & 1;
+  if (c->p_cur) {  // keep pointers canonical for the graphs of the next phase / solve
+    LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[B_P1], c->buf[TL_P]);
+    c->p_cur = 0;
+  }
+  return TL_OK;
+}
+
+static int fetch_cg_coefficients(tl_ctx *c, int iters, std::vector<double> &al, std::vector<double> &be) {
+  std::vector<double> rr(iters + 1), pw(iters + 1);
+  CU(c, cudaMemcpyAsync(rr.data(), c->hist_rr, (iters + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(pw.data(), c->hist_pw, (iters + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  al.resize(iters); be.resize(iters);
+  for (int t = 1; t <= iters; t++) {
+    al[t - 1] = rr[t - 1] / pw[t];   // CG.jl:35
+    be[t - 1] = rr[t] / rr[t - 1];   // CG.jl:39
+  }
+  return TL_OK;
+}
+
+static void finish_timing(tl_ctx *c, tl_solve_info *info, long long launches0) {
+  cudaEventRecord(c->ev_stop, c->stream);
+  cudaEventSynchronize(c->ev_stop);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop);
+  info->solve_ms = ms;
+  info->kernel_launches = c->launches - launches0;
+}
+
+extern "C" int tl_cg_solve(tl_ctx *c, int coef, double rx, double ry, double eps, int max_iters,
+                           tl_solve_info *info, double *cg_alphas, double *cg_betas) {
+  if (!c || !info) return TL_ERR_ARG;
+  memset(info, 0, sizeof *info);
+  CU(c, cudaSetDevice(c->device));
+  max_iters = std::min(max_iters, c->max_iters);
+  const long long l0 = c->launches;
+  CU(c, cudaEventRecord(c->ev_start, c->stream));
+  StopCfg cfg{max_iters, TL_CONV_SQRT, INT_MAX, 0, eps, 0.0};
+  TRY(solve_preamble(c, coef, rx, ry, cfg));
+  SolveState fin;
+  TRY(cg_phase(c, &fin));
+  TRY(cg_flush(c, fin.iter, true));
+  // hist_rr[iter] is written by the flush kernel
+  std::vector<double> al, be;
+  TRY(fetch_cg_coefficients(c, fin.iter, al, be));
+  finish_timing(c, info, l0);
+  if (cg_alphas) memcpy(cg_alphas, al.data(), al.size() * sizeof(double));
+  if (cg_betas) memcpy(cg_betas, be.data(), be.size() * sizeof(double));
+  info->iters = info->cg_iters = fin.iter;
+  info->error = fin.iter > 0 ? fin.red_rr : TL_ERROR_START;
+  return TL_OK;
+}
+
+static ChebyParams cheby_params(tl_ctx *c) {
+  ChebyParams P;
+  P.g = c->g; P.t = c->tiling; P.st = c->st; P.alphas = c->ch_alphas; P.betas = c->ch_betas;
+  P.u0 = c->buf[TL_U0]; P.ua = c->buf[TL_U]; P.ub = c->buf[B_U1]; P.p = c->buf[TL_P];
+  P.w = c->buf[TL_W]; P.r = c->buf[TL_R]; P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
+  return P;
+}
+
+static int enqueue_cheby_iteration(tl_ctx *c) {
+  if (c->nranks > 1) {
+    TRY(tile_barrier(c));
+    TRY(pull_halo(c, TL_U, 1));
+    TRY(pull_halo(c, B_U1, 1));
+    TRY(tile_barrier(c));
+  }
+  k_cheby_fused<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cheby_params(c));
+  CHECK_LAUNCH(c);
+  if (c->nranks > 1) TRY(allreduce(c, &c->st->red_norm, 1));
+  c->launches++;
+  return TL_OK;
+}
+
+// common switch bookkeeping of Cheby.solve!/PPCG.solve! (Cheby.jl:25-29, PPCG.jl:25-30)
+static StopCfg switch_cfg(int max_iters, double eps, int presteps, double epslim, int errorswitch) {
+  StopCfg cfg;
+  cfg.max_iters = max_iters;
+  cfg.conv_mode = TL_CONV_ABS;
+  cfg.first_it = 0;
+  cfg.eps = eps;
+  cfg.switch_min = errorswitch ? TL_CGEIGENITERS : std::max(presteps, 0);
+  cfg.switch_thresh = errorswitch ? epslim : TL_ERROR_SWITCH_MAX;
+  if (cfg.switch_min < 1) cfg.switch_min = 1;   // `error` is ERROR_START until one CG iteration ran
+  return cfg;
+}
+
+extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double eps, int max_iters, int presteps,
+                              double epslim, int errorswitch, tl_solve_info *info) {
+  if (!c || !info) return TL_ERR_ARG;
+  memset(info, 0, sizeof *info);
+  CU(c, cudaSetDevice(c->device));
+  if (c->nranks > 1) return tl_fail(c, TL_ERR_STATE, "tl_cheby_solve: tiled Chebyshev not wired yet");
+  max_iters = std::min(max_iters, c->max_iters);
+  const long long l0 = c->launches;
+  CU(c, cudaEventRecord(c->ev_start, c->stream));
+  const StopCfg cfg = switch_cfg(max_iters, eps, presteps, epslim, errorswitch);
+  TRY(solve_preamble(c, coef, rx, ry, cfg));
+  SolveState fin;
+  TRY(cg_phase(c, &fin));
+  TRY(cg_flush(c, fin.iter, true));
+  const int cgit = fin.iter;
+  info->cg_iters = cgit;
+  info->iters = cgit;
+  info->error = cgit > 0 ? fin.red_rr : TL_ERROR_START;
+  const bool converged = cgit > 0 && fabs(fin.red_rr) < eps;
+  if (converged || cgit >= max_iters) { finish_timing(c, info, l0); return TL_OK; }
+
+  // ---- switch: eigenvalues!, coef!  (Cheby.jl:66-67 with Appendix A #14) ----
+  std::vector<double> al, be;
+  TRY(fetch_cg_coefficients(c, cgit, al, be));
+  double eigmin = 0, eigmax = 0;
+  const int erc = tl::eigenvalues(al.data(), be.data(), cgit, &eigmin, &eigmax);
+  info->eigmin = eigmin; info->eigmax = eigmax;
+  if (erc) { finish_timing(c, info, l0); return tl_fail(c, TL_ERR_EIGEN, "Negative eigenvalue found: (%g, %g)", eigmin, eigmax); }
+  const int ncoef = std::max(1, std::min(max_iters - cgit, c->max_iters));
+  std::vector<double> cha(ncoef + 2, 0.0), chb(ncoef + 2, 0.0);
+  const double theta = tl::cheby_coef(eigmin, eigmax, ncoef, cha.data(), chb.data());
+  CU(c, cudaMemcpyAsync(c->ch_alphas, cha.data(), (ncoef + 2) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->ch_betas, chb.data(), (ncoef + 2) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k_state_cheby<<<1, 1, 0, c->stream>>>(c->st, theta, eps, cgit + 1, max_iters);
+  c->launches++;
+  CHECK_LAUNCH(c);
+  // both u buffers must agree outside the cells the fused kernel writes
+  LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[TL_U], c->buf[B_U1]);
+  // Cheby.init! field part + bb
+  k_cheby_fused<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cheby_params(c));
+  c->launches++;
+  CHECK_LAUNCH(c);
+  double bb = 0.0, error = 0.0;
+  TRY(read_scalars(c, &c->st->red_norm, 1, &bb));
+  // first main step with the norm, then Cheby.calciter
+  TRY(enqueue_cheby_iteration(c));
+  TRY(read_scalars(c, &c->st->red_norm, 1, &error));
+  const int est = tl::cheby_calc_iter(eigmin, eigmax, error, bb);
+  info->est_iters = est;
+  k_state_set_est<<<1, 1, 0, c->stream>>>(c->st, est);
+  c->launches++;
+  CHECK_LAUNCH(c);
+  auto enq = [&]() { return enqueue_cheby_iteration(c); };
+  auto stop = [&](const SolveState &s) {
+    return s.cheby_done || (s.cheby_tt0 + s.cheby_step - 1 > s.cheby_max_tt);
+  };
+  TRY(run_chunks(c, &c->g_cheby, &c->g_cheby_iters, c->graph_iters, 1, enq, stop, &fin));
+  c->u_cur = fin.cheby_step & 1;
+  if (c->u_cur) {
+    LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[B_U1], c->buf[TL_U]);
+    c->u_cur = 0;
+  }
+  finish_timing(c, info, l0);
+  info->cheby_iters = fin.cheby_step - 1;
+  info->iters = cgit + info->cheby_iters;
+  info->error = fin.red_norm;
+  return TL_OK;
+}
+
+static PpcgUrParams ppcg_ur_params(tl_ctx *c) {
+  PpcgUrParams P;
+  P.g = c->g; P.t = c->tiling; P.st = c->st; P.hist_pw = c->hist_pw;
+  P.p0 = c->buf[TL_P]; P.p1 = c->buf[B_P1]; P.w = c->buf[TL_W]; P.u = c->buf[TL_U]; P.r = c->buf[TL_R];
+  P.sd0 = c->buf[TL_SD];
+  return P;
+}
+static PpcgInnerParams ppcg_inner_params(tl_ctx *c) {
+  PpcgInnerParams P;
+  P.g = c->g; P.t = c->tiling; P.st = c->st; P.alphas = c->ch_alphas; P.betas = c->ch_betas;
+  P.sda = c->buf[TL_SD]; P.sdb = c->buf[B_SD1]; P.r = c->buf[TL_R]; P.u = c->buf[TL_U];
+  P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
+  return P;
+}
+
+static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps) {
+  k_cg_fused_w<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
+  CHECK_LAUNCH(c);
+  k_ppcg_ur_sd<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_ur_params(c));
+  CHECK_LAUNCH(c);
+  for (int pp = 0; pp < inner_steps; pp++) {
+    k_ppcg_inner<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_inner_params(c));
+    CHECK_LAUNCH(c);
+  }
+  c->launches += 2 + inner_steps;
+  return TL_OK;
+}
+
+extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double eps, int max_iters, int presteps,
+                             double epslim, int errorswitch, int inner_steps, tl_solve_info *info) {
+  if (!c || !info || inner_steps < 1) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_solve: bad argument");
+  memset(info, 0, sizeof *info);
+  CU(c, cudaSetDevice(c->device));
+  if (c->nranks > 1) return tl_fail(c, TL_ERR_STATE, "tl_ppcg_solve: tiled PPCG not wired yet");
+  max_iters = std::min(max_iters, c->max_iters);
+  const long long l0 = c->launches;
+  CU(c, cudaEventRecord(c->ev_start, c->stream));
+  StopCfg cfg = switch_cfg(max_iters, eps, presteps, epslim, errorswitch);
+  TRY(solve_preamble(c, coef, rx, ry, cfg));
+  SolveState fin;
+  TRY(cg_phase(c, &fin));
+  TRY(cg_flush(c, fin.iter, true));
+  const int cgit = fin.iter;
+  info->cg_iters = cgit;
+  info->iters = cgit;
+  info->error = cgit > 0 ? fin.red_rr : TL_ERROR_START;
+  const bool converged = cgit > 0 && fabs(fin.red_rr) < eps;
+  if (converged || cgit >= max_iters) { finish_timing(c, info, l0); return TL_OK; }
+
+  // ---- switch (PPCG.jl:39-45 with Appendix A #14, #19) ----
+  std::vector<double> al, be;
+  TRY(fetch_cg_coefficients(c, cgit, al, be));
+  double eigmin = 0, eigmax = 0;
+  const int erc = tl::eigenvalues(al.data(), be.data(), cgit, &eigmin, &eigmax);
+  info->eigmin = eigmin; info->eigmax = eigmax;
+  if (erc) { finish_timing(c, info, l0); return tl_fail(c, TL_ERR_EIGEN, "Negative eigenvalue found: (%g, %g)", eigmin, eigmax); }
+  std::vector<double> cha(inner_steps + 2, 0.0), chb(inner_steps + 2, 0.0);
+  const double theta = tl::cheby_coef(eigmin, eigmax, inner_steps, cha.data(), chb.data());
+  CU(c, cudaMemcpyAsync(c->ch_alphas, cha.data(), (inner_steps + 2) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->ch_betas, chb.data(), (inner_steps + 2) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TRY(residual_async(c));                                   // PPCG.jl:59
+  TRY(halo_update_buf(c, TL_P, 1));                         // PPCG.jl:60
+  TRY(norm2_async(c, TL_R, &c->st->red_rr));                // Appendix A #19: rro = sum r^2
+  cfg.first_it = cgit;
+  cfg.switch_min = INT_MAX;
+  k_state_begin<<<1, 1, 0, c->stream>>>(c->st, cfg, cgit, theta, inner_steps);
+  c->launches++;
+  CHECK_LAUNCH(c);
+  auto enq = [&]() { return enqueue_ppcg_outer(c, inner_steps); };
+  auto stop = [&](const SolveState &s) { return tl_should_stop(s.iter, s.red_rr, s.cfg); };
+  const int chunk = std::max(1, c->graph_iters / 4);
+  if (c->g_ppcg && c->g_ppcg_inner != inner_steps) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
+  c->g_ppcg_inner = inner_steps;
+  TRY(run_chunks(c, &c->g_ppcg, &c->g_ppcg_iters, chunk, 2 + inner_steps, enq, stop, &fin));
+  TRY(cg_flush(c, fin.iter, false));
+  c->sd_cur = inner_steps & 1;
+  if (c->sd_cur) {
+    LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[B_SD1], c->buf[TL_SD]);
+    c->sd_cur = 0;
+  }
+  finish_timing(c, info, l0);
+  info->cheby_iters = fin.iter - cgit;
+  info->inner_total = info->cheby_iters * inner_steps;
+  info->iters = fin.iter;
+  info->error = fin.red_rr;
+  return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// measurement helper
+// ---------------------------------------------------------------------------------------
+__global__ void k_state_for_timing(SolveState *st, double *hist_rr, double *hist_pw, double *cha, double *chb, int n) {
+  StopCfg cfg{INT_MAX, TL_CONV_ABS, INT_MAX, 0, 0.0, 0.0};
+  st->cfg = cfg;
+  st->iter = 2;
+  st->red_rr = 1.0; st->red_pw = 1e300;
+  hist_rr[1] = 1.0; hist_rr[2] = 1.0; hist_pw[2] = 1e300; hist_pw[3] = 1e300;
+  st->theta = 1.0; st->eps_cheby = 0.0; st->cheby_step = 1; st->cheby_done = 0; st->cheby_est = INT_MAX;
+  st->cheby_tt0 = 1; st->cheby_max_tt = INT_MAX; st->inner_steps = INT_MAX; st->inner_pp = 0; st->counter = 0u;
+  for (int i = 0; i < n; i++) { cha[i] = 0.5; chb[i] = 1e-3; }
+}
+
+extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *avg_ms) {
+  if (!c || !kernel || reps < 1 || !avg_ms) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  const std::string k(kernel);
+  reps = std::min(reps, c->max_iters - 4);
+  k_state_for_timing<<<1, 1, 0, c->stream>>>(c->st, c->hist_rr, c->hist_pw, c->ch_alphas, c->ch_betas, c->max_iters);
+  CHECK_LAUNCH(c);
+  auto launch = [&]() -> int {
+    if (k == "cg_fused_w") k_cg_fused_w<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
+    else if (k == "cg_fused_w_nou") k_cg_fused_w<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
+    else if (k == "cg_fused_r") k_cg_fused_r<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
+    else if (k == "cheby_fused") k_cheby_fused<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cheby_params(c));
+    else if (k == "ppcg_inner") k_ppcg_inner<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_inner_params(c));
+    else return tl_fail(c, TL_ERR_ARG, "tl_time_kernel: unknown kernel %s", kernel);
+    c->launches++;
+    return TL_OK;
+  };
+  for (int i = 0; i < 3; i++) TRY(launch());
+  CHECK_LAUNCH(c);
+  if (k == "cg_fused_r") {  // B advances the iteration counter: rewind it
+    k_state_for_timing<<<1, 1, 0, c->stream>>>(c->st, c->hist_rr, c->hist_pw, c->ch_alphas, c->ch_betas, c->max_iters);
+  }
+  CU(c, cudaEventRecord(c->ev_start, c->stream));
+  for (int i = 0; i < reps; i++) TRY(launch());
+  CU(c, cudaEventRecord(c->ev_stop, c->stream));
+  CU(c, cudaEventSynchronize(c->ev_stop));
+  CHECK_LAUNCH(c);
+  float ms = 0.f;
+  CU(c, cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop));
+  *avg_ms = ms / reps;
+  return TL_OK;
+}
+
+extern "C" int tl_timer_start(tl_ctx *c) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaEventRecord(c->ev_t0, c->stream));
+  return TL_OK;
+}
+
+extern "C" int tl_timer_stop(tl_ctx *c, double *elapsed_ms) {
+  if (!c || !elapsed_ms) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventRecord(c->ev_t1, c->stream));
+  CU(c, cudaEventSynchronize(c->ev_t1));
+  float ms = 0.f;
+  CU(c, cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+  *elapsed_ms = ms;
+  return TL_OK;
+}
+
+extern "C" int tl_launch_count(tl_ctx *c, long long *count) {
+  if (!c || !count) return TL_ERR_ARG;
+  *count = c->launches;
+  return TL_OK;
+}

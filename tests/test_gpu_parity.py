@@ -1,0 +1,267 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle.  Needs a B200: -m gpu.
+
+Bars (BASELINE.json north_star): identical iteration count (+-1 where reduction order
+differs), per-step field summaries within 1e-10 relative, final u within 1e-9 max relative
+error.  Element-wise kernels are held to bit-exactness (same expression order, no FMA
+contraction on either side)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import tealeaf_jl_b200 as tl
+from conftest import classic_settings
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.json")
+U_TOL = 1e-9        # final u, max relative error (north_star)
+SUMMARY_TOL = 1e-10  # vol / mass / ie / temp, relative (north_star)
+
+
+def _oracle():
+    from oracle.oracle import OracleChunk
+    return OracleChunk
+
+
+def _device():
+    from tealeaf_jl_b200.device import DeviceChunk
+    return DeviceChunk
+
+
+def run(backend, s, stepwise=False):
+    chunk, geom = tl.initialiseapp(s, backend=backend)
+    summaries = []
+    recs, final = tl.diffuse(chunk, s, geom, stepwise=stepwise,
+                             on_step=lambda rec: summaries.append(chunk.fieldsummary(geom.cell_volume)))
+    return chunk, recs, final, summaries
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def assert_parity(dev, ora, iter_slack=1, u_tol=U_TOL, fields=("u", "energy")):
+    dchunk, drecs, dfinal, dsum = dev
+    ochunk, orecs, ofinal, osum = ora
+    for dr, orr in zip(drecs, orecs):
+        assert abs(dr["iters"] - orr["iters"]) <= iter_slack, (dr, orr)
+    for ds, os_ in zip(dsum, osum):
+        for a, b in zip(ds, os_):
+            assert abs(a - b) <= SUMMARY_TOL * abs(b), (ds, os_)
+    for f in fields:
+        assert rel(dchunk.get_field(f), ochunk.get_field(f)) < u_tol, f
+
+
+# ---------------------------------------------------------------------------------------------
+# per-function kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx,ny,hd,coef", [(64, 64, 2, 1), (70, 50, 2, 1), (129, 65, 2, 2), (10, 10, 2, 1),
+                                           (33, 47, 1, 1), (96, 40, 3, 2), (1, 1, 2, 1), (2, 300, 2, 1)])
+def test_kernels_bitwise(nx, ny, hd, coef):
+    s = classic_settings(nx, ny=ny, steps=1, halodepth=hd, coefficient=coef)
+    rx, ry = s.dtinit / s.dx ** 2, s.dtinit / s.dy ** 2
+    chunks = []
+    for backend in (_device(), _oracle()):
+        c, geom = tl.initialiseapp(s, backend=backend)
+        tl.haloupdate(c, s, 1, ["energy", "density"])
+        chunks.append(c)
+    d, o = chunks
+    for f in ("density", "energy0", "energy"):
+        np.testing.assert_array_equal(d.get_field(f), o.get_field(f), err_msg=f)
+    rro_d, rro_o = d.cg_init(coef, rx, ry), o.cg_init(coef, rx, ry)
+    for f in ("u", "w", "r", "p", "kx", "ky"):
+        np.testing.assert_array_equal(d.get_field(f), o.get_field(f), err_msg=f"cg_init {f}")
+    assert abs(rro_d - rro_o) <= 1e-13 * abs(rro_o)
+    for c in (d, o):
+        c.haloupdate(["u", "p"], 1)
+        c.copyu()
+    np.testing.assert_array_equal(d.get_field("p"), o.get_field("p"))
+    np.testing.assert_array_equal(d.get_field("u0"), o.get_field("u0"))
+    pw_d, pw_o = d.cg_w(), o.cg_w()
+    np.testing.assert_array_equal(d.get_field("w"), o.get_field("w"), err_msg="cg_w")
+    assert abs(pw_d - pw_o) <= 1e-13 * abs(pw_o)
+    alpha = rro_o / pw_o
+    rrn_d, rrn_o = d.cg_ur(alpha), o.cg_ur(alpha)
+    np.testing.assert_array_equal(d.get_field("u"), o.get_field("u"), err_msg="cg_ur u")
+    np.testing.assert_array_equal(d.get_field("r"), o.get_field("r"), err_msg="cg_ur r")
+    assert abs(rrn_d - rrn_o) <= 1e-13 * abs(rrn_o)
+    beta = rrn_o / rro_o
+    for c in (d, o):
+        c.cg_p(beta)
+        c.haloupdate(["u", "p"], 1)
+    np.testing.assert_array_equal(d.get_field("p"), o.get_field("p"), err_msg="cg_p")
+    # Chebyshev / PPCG building blocks with arbitrary coefficients
+    theta = 3.0
+    bb_d, bb_o = d.cheby_init(theta), o.cheby_init(theta)
+    assert abs(bb_d - bb_o) <= 1e-13 * abs(bb_o)
+    e_d, e_o = d.cheby_iterate(0.4, 0.03, True, 0.0), o.cheby_iterate(0.4, 0.03, True, 0.0)
+    assert abs(e_d - e_o) <= 1e-13 * abs(e_o)
+    for f in ("u", "w", "r", "p"):
+        np.testing.assert_array_equal(d.get_field(f), o.get_field(f), err_msg=f"cheby {f}")
+    for c in (d, o):
+        c.ppcg_init_sd(theta)
+        c.ppcg_inner([0.3, 0.2, 0.1], [0.05, 0.04, 0.03], 3)
+    for f in ("u", "r", "sd"):
+        np.testing.assert_array_equal(d.get_field(f), o.get_field(f), err_msg=f"ppcg {f}")
+    assert abs(d.norm2("r") - o.norm2("r")) <= 1e-13 * abs(o.norm2("r"))
+    for c in (d, o):
+        c.solvefinished(True)
+    for f in ("r", "energy"):
+        np.testing.assert_array_equal(d.get_field(f), o.get_field(f), err_msg=f"solvefinished {f}")
+    sd, so = d.fieldsummary(0.37), o.fieldsummary(0.37)
+    for a, b in zip(sd, so):
+        assert abs(a - b) <= 1e-13 * abs(b)
+
+
+def test_halo_update_depths_and_roundtrip():
+    D = _device()
+    rng = np.random.default_rng(1)
+    for hd, depth in ((2, 1), (2, 2), (3, 3), (1, 1)):
+        nx, ny = 37, 21
+        c = D(nx, ny, hd, 100)
+        a = np.asfortranarray(rng.standard_normal((nx + 2 * hd, ny + 2 * hd)))
+        c.set_field("sd", a)
+        np.testing.assert_array_equal(c.get_field("sd"), a)   # H2D/D2H round trip, halos included
+        c.haloupdate(["sd"], depth)
+        want = a.copy(order="F")
+        from tealeaf_jl_b200.chunk import reflect_halo_host
+        reflect_halo_host(want, hd, depth)
+        np.testing.assert_array_equal(c.get_field("sd"), want)
+        c.close()
+
+
+def test_errors_are_reported_not_thrown():
+    from tealeaf_jl_b200.lib import TeaLeafError
+    c = _device()(16, 16, 2, 50)
+    with pytest.raises(TeaLeafError) as e:
+        c.cg_init(3, 1.0, 1.0)            # CG.jl:48-50
+    assert "Coefficient 3 is not valid" in str(e.value)
+    with pytest.raises(TeaLeafError):
+        c.haloupdate(["u"], 5)            # deeper than the halo (A#2: would index out of bounds)
+    c.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# whole solves
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver", ["cg", "cheby", "ppcg"])
+def test_stepwise_device_matches_oracle(solver):
+    s = lambda: classic_settings(64, ny=48, steps=1, solver=solver)
+    dev = run(_device(), s(), stepwise=True)
+    ora = run(_oracle(), s(), stepwise=True)
+    assert_parity(dev, ora, iter_slack=1, fields=("u", "energy", "p", "w"))
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 64), (128, 128), (200, 120), (10, 10), (65, 33), (257, 19), (1, 40), (3, 3)])
+def test_fused_cg_matches_oracle(nx, ny):
+    s = lambda: classic_settings(nx, ny=ny, steps=2, solver="cg")
+    dev = run(_device(), s())
+    ora = run(_oracle(), s())
+    assert_parity(dev, ora, fields=("u", "energy", "u0", "p", "kx", "ky"))
+    # the true residual (residual!, run by solvefinished!) is tiny on both
+    assert np.abs(dev[0].get_field("r")).max() < 1e-10
+
+
+@pytest.mark.parametrize("nx,ny", [(128, 128), (96, 160), (65, 70)])
+def test_fused_cheby_matches_oracle(nx, ny):
+    s = lambda: classic_settings(nx, ny=ny, steps=2, solver="cheby")
+    dev = run(_device(), s())
+    ora = run(_oracle(), s())
+    for dr, orr in zip(dev[1], ora[1]):
+        assert dr["cg_iters"] == orr["cg_iters"]
+        assert dr["est_iters"] == orr["est_iters"]
+        assert abs(dr["eigmin"] / orr["eigmin"] - 1) < 1e-10 and abs(dr["eigmax"] / orr["eigmax"] - 1) < 1e-10
+    assert_parity(dev, ora, iter_slack=0, fields=("u", "energy", "p", "w", "r"))
+
+
+@pytest.mark.parametrize("nx,ny,inner", [(128, 128, 10), (96, 160, 4), (65, 70, 7)])
+def test_fused_ppcg_matches_oracle(nx, ny, inner):
+    s = lambda: classic_settings(nx, ny=ny, steps=2, solver="ppcg", ppcginnersteps=inner)
+    dev = run(_device(), s())
+    ora = run(_oracle(), s())
+    for dr, orr in zip(dev[1], ora[1]):
+        assert dr["cg_iters"] == orr["cg_iters"]
+        assert dr["inner_total"] == orr["inner_total"]
+    assert_parity(dev, ora, iter_slack=0, fields=("u", "energy", "p", "sd"))
+
+
+def test_errorswitch_and_maxiters_paths():
+    for solver in ("cheby", "ppcg"):
+        s = lambda: classic_settings(96, steps=1, solver=solver, errorswitch=True, epslim=1e-3)
+        assert_parity(run(_device(), s()), run(_oracle(), s()), iter_slack=0)
+    for solver, cap in (("cg", 17), ("cheby", 45), ("ppcg", 33)):
+        s = lambda: classic_settings(96, steps=1, solver=solver, maxiters=cap)
+        dev, ora = run(_device(), s()), run(_oracle(), s())
+        assert dev[1][0]["iters"] == ora[1][0]["iters"] == cap
+        assert rel(dev[0].get_field("u"), ora[0].get_field("u")) < 1e-9
+
+
+def test_fused_and_stepwise_device_paths_agree():
+    s = lambda: classic_settings(150, ny=90, steps=1, solver="cg")
+    a, b = run(_device(), s()), run(_device(), s(), stepwise=True)
+    assert abs(a[1][0]["iters"] - b[1][0]["iters"]) <= 1
+    assert rel(a[0].get_field("u"), b[0].get_field("u")) < 1e-11
+
+
+def test_cg_coefficients_are_returned():
+    s = classic_settings(64, steps=1)
+    d, _ = tl.initialiseapp(s, backend=_device())
+    o, _ = tl.initialiseapp(classic_settings(64, steps=1), backend=_oracle())
+    rx, ry = s.dtinit / s.dx ** 2, s.dtinit / s.dy ** 2
+    for c in (d, o):
+        tl.haloupdate(c, s, 1, ["energy", "density"])
+    info = d.cg_solve(s, rx, ry)
+    o.cg_solve(s, rx, ry)
+    n = min(info["iters"], 40)
+    np.testing.assert_allclose(d.cgalpha[:n], o.cgalpha[:n], rtol=1e-9)
+    np.testing.assert_allclose(d.cgbeta[:n], o.cgbeta[:n], rtol=1e-9)
+
+
+def test_run_to_run_determinism():
+    outs = []
+    for _ in range(2):
+        c, recs, final, _ = run(_device(), classic_settings(200, steps=1, solver="cg"))
+        outs.append((c.get_field("u"), recs[0]["iters"], final["temp"]))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])   # fixed-order reductions, no FP64 atomics
+    assert outs[0][1:] == outs[1][1:]
+
+
+@pytest.mark.parametrize("idx", range(12))
+def test_golden(idx):
+    with open(GOLDEN) as fh:
+        case = json.load(fh)["cases"][idx]
+    s = classic_settings(case["nx"], ny=case["ny"], steps=case["steps"], solver=case["solver"])
+    chunk, recs, final, summaries = run(_device(), s)
+    slack = 1 if case["solver"] == "cg" else 0
+    for r, want in zip(recs, case["iters"]):
+        assert abs(r["iters"] - want) <= slack, (r, want)
+    for got, want in zip(summaries, case["summaries"]):
+        for k, v in zip(("vol", "mass", "ie", "temp"), got):
+            assert abs(v - want[k]) <= SUMMARY_TOL * abs(want[k]), (k, v, want[k])
+    u = chunk.get_field("u")[2:-2, 2:-2]
+    probe = case["u_probe"]
+    assert abs(u.sum() - probe["sum"]) <= 1e-10 * abs(probe["sum"])
+    assert abs(u.max() - probe["max"]) <= 1e-9 * abs(probe["max"])
+    assert abs(u[case["nx"] // 2, case["ny"] // 2] - probe["center"]) <= 1e-9 * abs(probe["max"])
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json sizes; the serial oracle would take minutes here)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_4096_properties():
+    s = classic_settings(4096, steps=1, solver="cg")
+    chunk, geom = tl.initialiseapp(s, backend=_device())
+    recs, final = tl.diffuse(chunk, s, geom)
+    it = recs[0]["iters"]
+    assert 4000 < it < 5200            # ~1.1 N iterations (SURVEY Appendix C extrapolation)
+    u = chunk.get_field("u")[2:-2, 2:-2]
+    u0 = chunk.get_field("u0")[2:-2, 2:-2]
+    assert abs(u.sum() - u0.sum()) <= 1e-11 * abs(u0.sum())      # energy conservation
+    assert np.abs(chunk.get_field("r")).max() < 1e-9             # true residual after residual!
+    assert u.min() > 0
+    # halo of u reflects its interior (haloupdate! {u,p} at CG.jl:22)
+    full = chunk.get_field("u")
+    np.testing.assert_array_equal(full[1, 2:-2], full[2, 2:-2])
+    np.testing.assert_array_equal(full[2:-2, -2], full[2:-2, -3])
