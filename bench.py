@@ -313,9 +313,9 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle.oracle import load
         threads = load().tlo_max_threads()
-        v, secs = cpu_cg_sample(4096, 12, threads)
+        v, secs = cpu_cg_sample(4096, 600, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"12 CG iterations of the same 4096x4096 deck ({secs:.1f} s), OpenMP oracle"}
+               "sample": f"600 CG iterations of the same 4096x4096 deck ({secs:.1f} s), OpenMP oracle"}
     elif rank == 0:
         cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "N>1: measured at N=1 only"}
 

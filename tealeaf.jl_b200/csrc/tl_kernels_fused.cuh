@@ -252,8 +252,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_flush(const CgAParam
   const double rr_cur = st->red_rr, rr_prev = P.hist_rr[it - 1];
   const double beta = rr_cur / rr_prev, alpha = rr_prev / P.hist_pw[it];
   if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_rr[it] = rr_cur;
-  const double *__restrict__ pin = (it & 1) ? P.p1 : P.p0;
-  double *__restrict__ pout = (it & 1) ? P.p0 : P.p1;
+  // pointwise, so done IN PLACE in the buffer kernel A of iteration `it` wrote: the current p
+  // stays buffer (it & 1) and a following phase (Chebyshev / PPCG) starts from it.
+  double *pin = (it & 1) ? P.p1 : P.p0;
+  double *pout = pin;
   const Geo g = P.g;
   const bool physL = g.phys & TL_PHYS_LEFT, physR = g.phys & TL_PHYS_RIGHT;
   const bool physB = g.phys & TL_PHYS_BOTTOM, physT = g.phys & TL_PHYS_TOP;
