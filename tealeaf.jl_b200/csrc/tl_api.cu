@@ -82,9 +82,11 @@ struct tl_ctx {
   cudaEvent_t ev[2]{}, ev_start = nullptr, ev_stop = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   int num_sms = 148;
   // tuning
-  int blocks_per_sm = 2, chunk_rows = 0, graph_iters = 8, use_graph = 1;
-  Tiling tiling{};
-  int fused_grid = 0, basic_grid = 0;
+  int blocks_per_sm = 2, pw_blocks_per_sm = 4, chunk_rows = 0, graph_iters = 8, use_graph = 1;
+  double l2_persist_mb = 0.0, l2_hit_scale = 1.0;
+  int l2_persist_field = TL_R;
+  Tiling tiling{}, pw_tiling{};   // stencil kernels / pointwise kernels
+  int fused_grid = 0, pw_grid = 0, basic_grid = 0;
   cudaGraphExec_t g_cg = nullptr, g_cheby = nullptr, g_ppcg = nullptr;
   int g_cg_iters = 0, g_cheby_iters = 0, g_ppcg_iters = 0, g_ppcg_inner = 0;
   long long launches = 0;
@@ -119,30 +121,60 @@ static double *field_ptr(tl_ctx *c, int f) {
   return c->buf[f];
 }
 
-static void compute_tiling(tl_ctx *c) {
+static void make_tiling(const tl_ctx *c, int blocks_per_sm, int chunk_rows, Tiling *tout, int *grid) {
   const Geo &g = c->g;
   Tiling t;
   t.nstrips = (g.nx + TL_STRIP - 1) / TL_STRIP;
   const int wpb = TL_FUSED_THREADS / 32;
-  const int target_warps = c->num_sms * c->blocks_per_sm * wpb;
+  const int target_warps = c->num_sms * blocks_per_sm * wpb;   // one co-resident wave
   int nchunks = std::max(1, target_warps / t.nstrips);
-  if (c->chunk_rows > 0) nchunks = (g.ny + c->chunk_rows - 1) / c->chunk_rows;
+  if (chunk_rows > 0) nchunks = (g.ny + chunk_rows - 1) / chunk_rows;
   nchunks = std::min(nchunks, g.ny);
+  nchunks = std::min(nchunks, std::max(1, TL_MAX_GRID * wpb / t.nstrips));  // bounded partials array
   t.rows_per_chunk = (g.ny + nchunks - 1) / nchunks;
   t.nchunks = (g.ny + t.rows_per_chunk - 1) / t.rows_per_chunk;
-  c->tiling = t;
-  c->fused_grid = (t.nstrips * t.nchunks + wpb - 1) / wpb;
-  if (c->fused_grid > TL_MAX_GRID) {  // keep the partials array bounded
-    const int max_warps = TL_MAX_GRID * wpb;
-    nchunks = std::max(1, max_warps / t.nstrips);
-    t.rows_per_chunk = (g.ny + nchunks - 1) / nchunks;
-    t.nchunks = (g.ny + t.rows_per_chunk - 1) / t.rows_per_chunk;
-    c->tiling = t;
-    c->fused_grid = (t.nstrips * t.nchunks + wpb - 1) / wpb;
-  }
+  *tout = t;
+  *grid = (t.nstrips * t.nchunks + wpb - 1) / wpb;
+}
+
+static void compute_tiling(tl_ctx *c) {
+  const Geo &g = c->g;
+  make_tiling(c, c->blocks_per_sm, c->chunk_rows, &c->tiling, &c->fused_grid);
+  make_tiling(c, c->pw_blocks_per_sm, 0, &c->pw_tiling, &c->pw_grid);
   const long cells = (long)(g.nx + 2 * g.hd) * (g.ny + 2 * g.hd);
   long nb = (cells + TL_BASIC_THREADS - 1) / TL_BASIC_THREADS;
   c->basic_grid = (int)std::max(1L, std::min<long>(nb, (long)c->num_sms * 8));
+}
+
+// Optional L2 residency: marks (part of) one field as persisting in the 126 MB L2 through the
+// stream's access-policy window, so that its HBM traffic disappears when the mesh is small
+// enough (4096^2: one field is 134.5 MB).  Captured graphs inherit the window.
+static int apply_l2_policy(tl_ctx *c) {
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof attr);
+  if (c->l2_persist_mb <= 0.0) {
+    attr.accessPolicyWindow.num_bytes = 0;
+    CU(c, cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    cudaCtxResetPersistingL2Cache();
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    return TL_OK;
+  }
+  cudaDeviceProp prop;
+  CU(c, cudaGetDeviceProperties(&prop, c->device));
+  size_t want = (size_t)(c->l2_persist_mb * 1e6);
+  const size_t carve = std::min(want, (size_t)prop.persistingL2CacheMaxSize);
+  CU(c, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+  const Geo &g = c->g;
+  char *base = (char *)(c->buf[c->l2_persist_field] - (size_t)g.hd * g.pitch - TL_XPAD);
+  size_t bytes = c->rows * (size_t)g.pitch * sizeof(double);
+  bytes = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+  attr.accessPolicyWindow.base_ptr = base;
+  attr.accessPolicyWindow.num_bytes = bytes;
+  attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve * c->l2_hit_scale / (double)bytes);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  CU(c, cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  return TL_OK;
 }
 
 static void destroy_graphs(tl_ctx *c) {
@@ -260,6 +292,10 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   if (!c || !name) return TL_ERR_ARG;
   const std::string n(name);
   if (n == "blocks_per_sm") c->blocks_per_sm = std::max(1, (int)value);
+  else if (n == "pw_blocks_per_sm") c->pw_blocks_per_sm = std::max(1, (int)value);
+  else if (n == "l2_persist_mb") c->l2_persist_mb = value;
+  else if (n == "l2_hit_scale") c->l2_hit_scale = value;
+  else if (n == "l2_persist_field") c->l2_persist_field = std::min(std::max(0, (int)value), (int)B_COUNT - 1);
   else if (n == "chunk_rows") c->chunk_rows = std::max(0, (int)value);
   else if (n == "graph_iters") c->graph_iters = std::max(1, (int)value);
   else if (n == "use_graph") c->use_graph = value != 0.0;
@@ -268,7 +304,7 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   cudaStreamSynchronize(c->stream);
   destroy_graphs(c);
   compute_tiling(c);
-  return TL_OK;
+  return apply_l2_policy(c);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -327,12 +363,18 @@ extern "C" int tl_comm_connect(tl_ctx *c, const void *all_blobs, const void *id1
   return TL_OK;
 }
 
-// sum over tiles of n doubles living in device memory (stream ordered)
-static int allreduce(tl_ctx *c, double *dev, int n) {
-  if (c->nranks == 1) return TL_OK;
+// sum over tiles of n doubles living in device memory (stream ordered); out of place when
+// src != dst.  With one tile it degenerates to a copy (or nothing).
+static int allreduce2(tl_ctx *c, const double *src, double *dst, int n);
+static int allreduce(tl_ctx *c, double *dev, int n) { return allreduce2(c, dev, dev, n); }
+static int allreduce2(tl_ctx *c, const double *src, double *dst, int n) {
+  if (c->nranks == 1) {
+    if (src != dst) CU(c, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return TL_OK;
+  }
   if (!c->comm_ready) return tl_fail(c, TL_ERR_STATE, "tile context used before tl_comm_connect");
 #ifdef TL_WITH_NCCL
-  ncclResult_t r = nccl_api().AllReduce(dev, dev, n, ncclDouble, ncclSum, c->nccl, c->stream);
+  ncclResult_t r = nccl_api().AllReduce(src, dst, n, ncclDouble, ncclSum, c->nccl, c->stream);
   if (r != ncclSuccess) return tl_fail(c, TL_ERR_COMM, "ncclAllReduce: %s", nccl_api().GetErrorString(r));
   return TL_OK;
 #else
@@ -651,12 +693,14 @@ static CgAParams cg_a_params(tl_ctx *c) {
   P.g = c->g; P.t = c->tiling; P.st = c->st; P.hist_rr = c->hist_rr; P.hist_pw = c->hist_pw;
   P.r = c->buf[TL_R]; P.p0 = c->buf[TL_P]; P.p1 = c->buf[B_P1]; P.u = c->buf[TL_U];
   P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.w = c->buf[TL_W]; P.partials = c->partials;
+  P.single = c->nranks == 1;
   return P;
 }
 static CgBParams cg_b_params(tl_ctx *c) {
   CgBParams P;
-  P.g = c->g; P.t = c->tiling; P.st = c->st; P.hist_pw = c->hist_pw;
+  P.g = c->g; P.t = c->pw_tiling; P.st = c->st; P.hist_pw = c->hist_pw;
   P.r = c->buf[TL_R]; P.w = c->buf[TL_W]; P.partials = c->partials;
+  P.single = c->nranks == 1;
   return P;
 }
 
@@ -670,10 +714,10 @@ static int enqueue_cg_iteration(tl_ctx *c) {
   }
   k_cg_fused_w<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
   CHECK_LAUNCH(c);
-  TRY(allreduce(c, &c->st->red_pw, 1));
-  k_cg_fused_r<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
+  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
+  k_cg_fused_r<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
   CHECK_LAUNCH(c);
-  TRY(allreduce(c, &c->st->red_rr, 1));
+  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
   c->launches += 2;
   return TL_OK;
 }
@@ -748,11 +792,20 @@ static int cg_phase(tl_ctx *c, SolveState *fin) {
 
 // flush the deferred p/u update of the last iteration and make buffer 0 the current p
 static int cg_flush(tl_ctx *c, int iters_done, bool update_u) {
-  if (update_u) k_cg_flush<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
-  else k_cg_flush<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
+  CgAParams P = cg_a_params(c);
+  P.t = c->pw_tiling;
+  if (update_u) k_cg_flush<true><<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
+  else k_cg_flush<false><<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
   c->launches++;
   CHECK_LAUNCH(c);
   c->p_cur = iters_done & 1;
+  if (c->nranks > 1) {
+    // haloupdate!(.., [:u,:p]) of the last iteration on the tile-internal sides
+    TRY(tile_barrier(c));
+    if (update_u) TRY(pull_halo(c, TL_U, 1));
+    TRY(pull_halo(c, c->p_cur ? B_P1 : TL_P, 1));
+    TRY(tile_barrier(c));
+  }
   if (c->p_cur) {  // keep pointers canonical for the graphs of the next phase / solve
     LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[B_P1], c->buf[TL_P]);
     c->p_cur = 0;
@@ -811,19 +864,21 @@ static ChebyParams cheby_params(tl_ctx *c) {
   P.g = c->g; P.t = c->tiling; P.st = c->st; P.alphas = c->ch_alphas; P.betas = c->ch_betas;
   P.u0 = c->buf[TL_U0]; P.ua = c->buf[TL_U]; P.ub = c->buf[B_U1]; P.p = c->buf[TL_P];
   P.w = c->buf[TL_W]; P.r = c->buf[TL_R]; P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
+  P.single = c->nranks == 1;
   return P;
 }
 
+// One Chebyshev iteration.  Tiled: the norm allreduce that ends every iteration (it re-publishes
+// the last norm on iterations that do not compute one) is also the rendezvous that orders the
+// next iteration's halo pull after the neighbours' kernels.
 static int enqueue_cheby_iteration(tl_ctx *c) {
   if (c->nranks > 1) {
-    TRY(tile_barrier(c));
     TRY(pull_halo(c, TL_U, 1));
     TRY(pull_halo(c, B_U1, 1));
-    TRY(tile_barrier(c));
   }
   k_cheby_fused<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cheby_params(c));
   CHECK_LAUNCH(c);
-  if (c->nranks > 1) TRY(allreduce(c, &c->st->red_norm, 1));
+  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_norm_local, &c->st->red_norm, 1));
   c->launches++;
   return TL_OK;
 }
@@ -846,7 +901,6 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
   if (!c || !info) return TL_ERR_ARG;
   memset(info, 0, sizeof *info);
   CU(c, cudaSetDevice(c->device));
-  if (c->nranks > 1) return tl_fail(c, TL_ERR_STATE, "tl_cheby_solve: tiled Chebyshev not wired yet");
   max_iters = std::min(max_iters, c->max_iters);
   const long long l0 = c->launches;
   CU(c, cudaEventRecord(c->ev_start, c->stream));
@@ -883,6 +937,7 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
   k_cheby_fused<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cheby_params(c));
   c->launches++;
   CHECK_LAUNCH(c);
+  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_norm_local, &c->st->red_norm, 1));
   double bb = 0.0, error = 0.0;
   TRY(read_scalars(c, &c->st->red_norm, 1, &bb));
   // first main step with the norm, then Cheby.calciter
@@ -894,11 +949,13 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
   c->launches++;
   CHECK_LAUNCH(c);
   auto enq = [&]() { return enqueue_cheby_iteration(c); };
-  auto stop = [&](const SolveState &s) {
-    return s.cheby_done || (s.cheby_tt0 + s.cheby_step - 1 > s.cheby_max_tt);
-  };
+  auto stop = [&](const SolveState &s) { return tl_cheby_should_stop(s); };
   TRY(run_chunks(c, &c->g_cheby, &c->g_cheby_iters, c->graph_iters, 1, enq, stop, &fin));
   c->u_cur = fin.cheby_step & 1;
+  if (c->nranks > 1) {   // haloupdate!(.., [:u]) of the last iteration on the tile-internal sides
+    TRY(pull_halo(c, c->u_cur ? B_U1 : TL_U, 1));
+    TRY(tile_barrier(c));
+  }
   if (c->u_cur) {
     LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[B_U1], c->buf[TL_U]);
     c->u_cur = 0;
@@ -912,7 +969,7 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
 
 static PpcgUrParams ppcg_ur_params(tl_ctx *c) {
   PpcgUrParams P;
-  P.g = c->g; P.t = c->tiling; P.st = c->st; P.hist_pw = c->hist_pw;
+  P.g = c->g; P.t = c->pw_tiling; P.st = c->st; P.hist_pw = c->hist_pw;
   P.p0 = c->buf[TL_P]; P.p1 = c->buf[B_P1]; P.w = c->buf[TL_W]; P.u = c->buf[TL_U]; P.r = c->buf[TL_R];
   P.sd0 = c->buf[TL_SD];
   return P;
@@ -922,18 +979,33 @@ static PpcgInnerParams ppcg_inner_params(tl_ctx *c) {
   P.g = c->g; P.t = c->tiling; P.st = c->st; P.alphas = c->ch_alphas; P.betas = c->ch_betas;
   P.sda = c->buf[TL_SD]; P.sdb = c->buf[B_SD1]; P.r = c->buf[TL_R]; P.u = c->buf[TL_U];
   P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
+  P.single = c->nranks == 1;
   return P;
 }
 
+// One PPCG outer iteration.  Tiled: depth-1 halos -- r, p before the matvec (ordered by the
+// preceding rr allreduce) and sd before every inner step (ordered by a 1-double rendezvous).
 static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps) {
+  if (c->nranks > 1) {
+    TRY(pull_halo(c, TL_R, 1));
+    TRY(pull_halo(c, TL_P, 1));
+    TRY(pull_halo(c, B_P1, 1));
+  }
   k_cg_fused_w<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
   CHECK_LAUNCH(c);
-  k_ppcg_ur_sd<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_ur_params(c));
+  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
+  k_ppcg_ur_sd<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_ur_params(c));
   CHECK_LAUNCH(c);
   for (int pp = 0; pp < inner_steps; pp++) {
+    if (c->nranks > 1) {
+      TRY(tile_barrier(c));
+      TRY(pull_halo(c, TL_SD, 1));
+      TRY(pull_halo(c, B_SD1, 1));
+    }
     k_ppcg_inner<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_inner_params(c));
     CHECK_LAUNCH(c);
   }
+  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
   c->launches += 2 + inner_steps;
   return TL_OK;
 }
@@ -943,7 +1015,6 @@ extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double e
   if (!c || !info || inner_steps < 1) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_solve: bad argument");
   memset(info, 0, sizeof *info);
   CU(c, cudaSetDevice(c->device));
-  if (c->nranks > 1) return tl_fail(c, TL_ERR_STATE, "tl_ppcg_solve: tiled PPCG not wired yet");
   max_iters = std::min(max_iters, c->max_iters);
   const long long l0 = c->launches;
   CU(c, cudaEventRecord(c->ev_start, c->stream));
@@ -1022,7 +1093,7 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
   auto launch = [&]() -> int {
     if (k == "cg_fused_w") k_cg_fused_w<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
     else if (k == "cg_fused_w_nou") k_cg_fused_w<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
-    else if (k == "cg_fused_r") k_cg_fused_r<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
+    else if (k == "cg_fused_r") k_cg_fused_r<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
     else if (k == "cheby_fused") k_cheby_fused<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cheby_params(c));
     else if (k == "ppcg_inner") k_ppcg_inner<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_inner_params(c));
     else return tl_fail(c, TL_ERR_ARG, "tl_time_kernel: unknown kernel %s", kernel);

@@ -50,7 +50,7 @@ struct SolveState {
   StopCfg cfg;
   int iter;             // completed CG-type iterations (CG.jl:18 `tt`, PPCG outer included)
   int cheby_step;       // completed Chebyshev kernels (init counts as step 0 -> 1)
-  int cheby_done;       // set when a Chebyshev norm met abs(error) < eps
+  int cheby_done;       // (unused: the stop rule is a pure function of the state)
   int cheby_est;        // Cheby.calciter estimate (uploaded by the host after the first step)
   int cheby_tt0;        // outer iteration number `tt` of Chebyshev step 1
   int cheby_max_tt;     // maxiters
@@ -61,6 +61,9 @@ struct SolveState {
   double red_pw;        // sum(p.w) of the latest matvec (after the allreduce when tiled)
   double red_rr;        // sum(r.r) after `iter` iterations (rro when iter == first_it)
   double red_norm;      // Chebyshev: latest sum(r.r);   cheby_init: bb = sum(u0.u0)
+  // this tile's parts: the kernels write *_local, the (out-of-place) allreduce publishes the
+  // global value -- idempotent when a launched-ahead kernel was a no-op
+  double red_pw_local, red_rr_local, red_norm_local;
   double red_aux[4];    // field summary / norm2 results
   double theta;
   double eps_cheby;

@@ -57,6 +57,7 @@ struct CgAParams {
   double *hist_rr; const double *hist_pw;
   const double *r; double *p0; double *p1; double *u; const double *kx; const double *ky; double *w;
   double *partials;
+  int single;   // 1: one tile -- the kernel publishes its sums itself (no allreduce follows)
 };
 
 template <bool UPDATE_U>
@@ -175,7 +176,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 2) k_cg_fused_w(const CgAPar
       Xm = Xc; Xc = Xn; XcE = XnE; pc = cur.p; kyc = cur.ky;
     }
   }
-  if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) st->red_pw = acc[0];
+  if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) {
+    st->red_pw_local = acc[0];
+    if (P.single) st->red_pw = acc[0];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -189,6 +193,7 @@ struct CgBParams {
   double *hist_pw;
   double *r; const double *w;
   double *partials;
+  int single;
 };
 
 __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBParams P) {
@@ -234,7 +239,8 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBPar
     }
   }
   if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) {
-    st->red_rr = acc[0];
+    st->red_rr_local = acc[0];
+    if (P.single) st->red_rr = acc[0];
     st->iter = it + 1;
   }
 }
@@ -295,7 +301,25 @@ struct ChebyParams {
   const double *u0; double *ua; double *ub; double *p; double *w; double *r;
   const double *kx; const double *ky;
   double *partials;
+  int single;   // 1: one tile, the kernel publishes its norm itself
 };
+
+// Was Chebyshev step `chebyiters` (1-based) a norm iteration?  Cheby.jl:40-51
+__host__ __device__ inline bool tl_cheby_is_norm_iter(int chebyiters, int tt0, int est) {
+  if (chebyiters < 1) return false;
+  if (chebyiters == 1) return true;
+  const int tt = tt0 + chebyiters - 1;
+  return (chebyiters >= est) && ((tt + 1) % 10 == 0);
+}
+// Stop rule of the Chebyshev loop after `step` kernels (init included), evaluated at the entry
+// of every kernel and by the host: converged on the last norm (Cheby.jl:57, after the
+// allreduce when tiled) or out of iterations.
+__host__ __device__ inline bool tl_cheby_should_stop(const SolveState &s) {
+  const int done_iters = s.cheby_step - 1;   // completed main steps
+  if (done_iters >= 1 && tl_cheby_is_norm_iter(done_iters, s.cheby_tt0, s.cheby_est) && fabs(s.red_norm) < s.eps_cheby)
+    return true;
+  return s.cheby_tt0 + s.cheby_step - 1 > s.cheby_max_tt;
+}
 
 template <bool FIRST>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, 2) k_cheby_fused(const ChebyParams P) {
@@ -310,12 +334,12 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 2) k_cheby_fused(const Cheby
     store_wr = true;
   } else {
     // `step` kernels done => this is chebyiters = step (init was step 0 -> 1), Cheby.jl:35-51
+    if (tl_cheby_should_stop(*st)) return;
     const int chebyiters = step;
     const int tt = st->cheby_tt0 + chebyiters - 1;
-    if (st->cheby_done || tt > st->cheby_max_tt) return;
     alpha = P.alphas[chebyiters];   // 1-based chebyα[chebyiters+1]
     beta = P.betas[chebyiters];
-    calc_norm = (chebyiters == 1) || ((chebyiters >= st->cheby_est) && ((tt + 1) % 10 == 0));
+    calc_norm = tl_cheby_is_norm_iter(chebyiters, st->cheby_tt0, st->cheby_est);
     store_wr = calc_norm || (tt == st->cheby_max_tt);
   }
   const double *__restrict__ uin = (step & 1) ? P.ub : P.ua;
@@ -405,9 +429,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 2) k_cheby_fused(const Cheby
   }
   if (calc_norm) {
     if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) {
-      st->red_norm = acc[0];
+      st->red_norm_local = acc[0];
+      if (P.single) st->red_norm = acc[0];   // tiled: k_stage_scalar + allreduce publish it
       st->cheby_step = step + 1;
-      if (!FIRST && fabs(acc[0]) < st->eps_cheby) st->cheby_done = 1;   // Cheby.jl:57
     }
   } else {
     // no reduction needed: only the ticket, so that the last block can advance the step
@@ -468,6 +492,7 @@ struct PpcgInnerParams {
   const double *alphas; const double *betas;
   double *sda; double *sdb; double *r; double *u; const double *kx; const double *ky;
   double *partials;
+  int single;
 };
 
 __global__ void __launch_bounds__(TL_FUSED_THREADS, 2) k_ppcg_inner(const PpcgInnerParams P) {
@@ -562,7 +587,8 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 2) k_ppcg_inner(const PpcgIn
   }
   if (last) {
     if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) {
-      st->red_rr = acc[0];      // PPCG.jl:88
+      st->red_rr_local = acc[0];      // PPCG.jl:88
+      if (P.single) st->red_rr = acc[0];
       st->iter = it + 1;
       st->inner_pp = pp + 1;
     }

@@ -1,0 +1,109 @@
+"""2-D domain decomposition: one process per GPU, one tile per process.
+
+The reference has a single `Chunk` and no decomposition ("Parallelism strategies
+in the reference: none"); its `haloupdate!` vocabulary ("exchange") comes from the MPI
+upstream.  Here the global `xcells x ycells` interior is cut into a `px x py` grid of tiles
+(y, the strided dimension, is split first so that most exchanged faces are contiguous rows).
+Plumbing is `torch.distributed` (NCCL on GPUs, gloo in the CPU tests); the data path is
+inside libtealeaf_b200: neighbours' edge cells are read directly from their memory over
+NVLink (CUDA-IPC mapped pointers), dot products are NCCL allreduces captured in the CUDA graphs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .chunk import HostGeometry, paint_states
+from .settings import Settings
+
+
+def grid_for(world: int):
+    """px x py for `world` ranks: 1x1, 1x2, 2x2, 2x4, else the squarest split."""
+    table = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+    if world in table:
+        return table[world]
+    px = int(np.floor(np.sqrt(world)))
+    while world % px:
+        px -= 1
+    return px, world // px
+
+
+def split(n: int, parts: int, idx: int):
+    """(offset, size) of piece `idx` when n cells are cut into `parts` nearly equal pieces."""
+    base, rem = divmod(n, parts)
+    size = base + (1 if idx < rem else 0)
+    off = idx * base + min(idx, rem)
+    return off, size
+
+
+def tile_of(rank: int, px: int, py: int, nx: int, ny: int):
+    """(x0, y0, tile_nx, tile_ny) of `rank` = cx + cy*px."""
+    cx, cy = rank % px, rank // px
+    x0, tnx = split(nx, px, cx)
+    y0, tny = split(ny, py, cy)
+    return x0, y0, tnx, tny
+
+
+def connect(chunk, dist):
+    """Exchange CUDA-IPC blobs and the NCCL id, then wire the tile to its neighbours."""
+    world = dist.get_world_size()
+    blobs = [None] * world
+    dist.all_gather_object(blobs, chunk.comm_export())
+    ident = [chunk.comm_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    chunk.comm_connect(blobs, ident[0])
+
+
+def create_tile(settings: Settings, dist, device: int, backend=None):
+    """`initialiseapp!` for this rank's tile.  Returns (chunk, geom, (px, py))."""
+    from .app import upload_initial_state
+    world, rank = dist.get_world_size(), dist.get_rank()
+    px, py = grid_for(world)
+    x0, y0, tnx, tny = tile_of(rank, px, py, settings.xcells, settings.ycells)
+    if backend is None:
+        from .device import DeviceChunk
+        backend = DeviceChunk
+    chunk = backend(tnx, tny, settings.halodepth, settings.maxiters, device=device, rank=rank, px=px, py=py)
+    connect(chunk, dist)
+    geom = HostGeometry(settings, tile=(x0, y0, tnx, tny))
+    upload_initial_state(chunk, settings, geom)
+    return chunk, geom, (px, py)
+
+
+def gather_field(chunk, name: str, settings: Settings, dist, dst: int = 0):
+    """Assemble the global (x, y) array of `name` (interior from every tile; halos from the
+    tiles that own the physical boundary) on rank `dst`."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    px, py = grid_for(world)
+    local = chunk.get_field(name)
+    parts = [None] * world if rank == dst else None
+    dist.gather_object(local, parts, dst=dst)
+    if rank != dst:
+        return None
+    return assemble(parts, px, py, settings.xcells, settings.ycells, settings.halodepth)
+
+
+def assemble(parts, px: int, py: int, nx: int, ny: int, hd: int) -> np.ndarray:
+    out = np.zeros((nx + 2 * hd, ny + 2 * hd), order="F")
+    for r, a in enumerate(parts):
+        x0, y0, tnx, tny = tile_of(r, px, py, nx, ny)
+        cx, cy = r % px, r // px
+        # interior plus whichever halo sides are physical
+        xl = 0 if cx == 0 else hd
+        xr = tnx + 2 * hd if cx == px - 1 else tnx + hd
+        yl = 0 if cy == 0 else hd
+        yr = tny + 2 * hd if cy == py - 1 else tny + hd
+        out[x0 + xl:x0 + xr, y0 + yl:y0 + yr] = a[xl:xr, yl:yr]
+    return out
+
+
+def paint_global_from_tiles(settings: Settings, px: int, py: int):
+    """Host-only helper (tests): paint every tile and assemble; must equal the 1-tile painting."""
+    dens, ener = [], []
+    for r in range(px * py):
+        g = HostGeometry(settings, tile=tile_of(r, px, py, settings.xcells, settings.ycells))
+        d, e, _ = paint_states(settings, g)
+        dens.append(d)
+        ener.append(e)
+    hd = settings.halodepth
+    return (assemble(dens, px, py, settings.xcells, settings.ycells, hd),
+            assemble(ener, px, py, settings.xcells, settings.ycells, hd))

@@ -1,0 +1,55 @@
+"""Tiled (2-D domain decomposition) runs.  The GPU test launches tests/mgpu_check.py under
+torchrun when the box has >= 2 GPUs; the CPU test covers the host-side plumbing with gloo."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import tealeaf_jl_b200 as tl
+from tealeaf_jl_b200 import dist as tld
+from conftest import classic_settings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(script, nproc, *args, timeout=900):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "tests", script), *args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+
+
+def test_decomposition_helpers():
+    assert tld.grid_for(1) == (1, 1) and tld.grid_for(2) == (1, 2) and tld.grid_for(4) == (2, 2) and tld.grid_for(8) == (2, 4)
+    assert tld.grid_for(6) == (2, 3)
+    for n, parts in ((10, 3), (4096, 4), (7, 7), (130, 4)):
+        pieces = [tld.split(n, parts, i) for i in range(parts)]
+        assert pieces[0][0] == 0 and sum(p[1] for p in pieces) == n
+        for a, b in zip(pieces, pieces[1:]):
+            assert a[0] + a[1] == b[0]
+    # tiles painted independently assemble to the single-chunk painting, halos included
+    s = classic_settings(50, ny=37)
+    from tealeaf_jl_b200.chunk import HostGeometry, paint_states
+    d, e, _ = paint_states(s, HostGeometry(s))
+    for px, py in ((1, 2), (2, 2), (2, 4), (3, 1)):
+        dt, et = tld.paint_global_from_tiles(s, px, py)
+        np.testing.assert_array_equal(dt, d)
+        np.testing.assert_array_equal(et, e)
+
+
+def test_gloo_world2_host_plumbing():
+    r = _torchrun("dist_cpu_worker.py", 2, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "dist_cpu_worker OK" in r.stdout
+
+
+@pytest.mark.gpu
+def test_tiled_solvers_match_oracle():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    r = _torchrun("mgpu_check.py", min(n, 8))
+    sys.stdout.write(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
