@@ -294,10 +294,16 @@ def run_b200(args):
     ka_ms = chunk.time_kernel("cg_fused_w", 30)
     kb_ms = chunk.time_kernel("cg_fused_r", 30)
     it_ms = solve_ms / max(iters, 1)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get(f"k_cg_fused_w@{tile_nx}x{tile_ny}")
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": "k_cg_fused_w<true>",
         "achieved": KERNEL_A_ALG_BYTES * tile_cells / (ka_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-        "frac": KERNEL_A_ALG_BYTES * tile_cells / (ka_ms * 1e-3) / 1e9 / peak, "traffic": None,
+        "frac": KERNEL_A_ALG_BYTES * tile_cells / (ka_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
         "peak_source": peak_src, "avg_launch_ms": ka_ms,
         "algorithmic_bytes_per_cell": KERNEL_A_ALG_BYTES, "physical_bytes_per_cell": KERNEL_A_PHYS_BYTES,
         "physical_gbs": KERNEL_A_PHYS_BYTES * tile_cells / (ka_ms * 1e-3) / 1e9,

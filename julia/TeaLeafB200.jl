@@ -1,0 +1,230 @@
+# TeaLeafB200.jl -- the reference-side binding of libtealeaf_b200.so (include/tealeaf_b200.h).
+#
+# Drop this file next to the reference's src/TeaLeaf.jl and `include` it after the solver
+# modules (see INTEGRATION.md).  Julia stays in charge of settings parsing (src/settings.jl),
+# state painting (src/chunk.jl:122-151), the timestep loop (src/TeaLeaf.jl:62-83) and the field
+# summary printout; the library owns the device-resident Chunk fields and every kernel.
+#
+# NOTE: there is no Julia binary in the environment this repository is built and tested in,
+# so this file is reviewed, not executed, there.  It is deliberately a 1:1 transliteration of
+# tealeaf.jl_b200/lib.py + device.py + solvers.py (which ARE executed by the test-suite against
+# the same C-ABI); every ccall below has the argument list of the matching ctypes signature.
+module TeaLeafB200
+
+using TeaLeaf
+using TeaLeaf.Kernels: ERROR_START
+
+const LIB = get(ENV, "TEALEAF_B200_LIB",
+                joinpath(@__DIR__, "..", "tealeaf.jl_b200", "csrc", "libtealeaf_b200.so"))
+
+# tl_field (include/tealeaf_b200.h) <-> Chunk field names (src/chunk.jl:25-38)
+const FIELD_ID = Dict(:density => 0, :energy0 => 1, :energy => 2, :u => 3, :u0 => 4, :p => 5,
+                      :r => 6, :w => 7, :kx => 8, :ky => 9, :sd => 10)
+
+# tl_solve_info
+struct SolveInfo
+    iters::Cint; cg_iters::Cint; cheby_iters::Cint; est_iters::Cint; inner_total::Cint; reserved::Cint
+    error::Cdouble; eigmin::Cdouble; eigmax::Cdouble; solve_ms::Cdouble; kernel_launches::Clonglong
+end
+
+"""
+Device-resident counterpart of `Chunk` (src/chunk.jl:19-60): same `x`, `y`, coefficient
+vectors; the 11 field matrices live in HBM behind `ctx`.
+"""
+mutable struct B200Chunk
+    ctx::Ptr{Cvoid}
+    x::Int
+    y::Int
+    halodepth::Int
+    volume::Float64            # dx*dy (src/chunk.jl:79: volume is uniform)
+    cgα::Vector{Float64}
+    cgβ::Vector{Float64}
+    eigmin::Float64
+    eigmax::Float64
+end
+
+function check(chunk::B200Chunk, rc::Cint)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:tl_last_error, LIB), Cstring, (Ptr{Cvoid},), chunk.ctx))
+    throw("libtealeaf_b200 error $(rc): $(msg)")   # the reference throws strings (CG.jl:49, kernels.jl:42)
+end
+
+"""
+    B200Chunk(settings; device = 0)
+
+`Chunk(settings)` (src/chunk.jl:68-89) on the GPU.
+"""
+function B200Chunk(set::Settings; device::Int = 0)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:tl_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint),
+               ctx, set.xcells, set.ycells, set.halodepth, set.maxiters, device)
+    rc == 0 || throw("tl_create failed ($(rc)): a B200 (sm_100) GPU is required, there is no CPU fallback")
+    chunk = B200Chunk(ctx[], set.xcells + 2set.halodepth, set.ycells + 2set.halodepth, set.halodepth,
+                      set.dx * set.dy, zeros(set.maxiters), zeros(set.maxiters), 0.0, 0.0)
+    finalizer(c -> ccall((:tl_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.ctx), chunk)
+    return chunk
+end
+
+Base.size(c::B200Chunk) = (c.x, c.y)
+
+# ---- field transfer: getfield/setfield of Chunk matrices -------------------------------------
+function upload!(chunk::B200Chunk, field::Symbol, a::Matrix{Float64})
+    size(a) == size(chunk) || throw(DimensionMismatch("field $(field)"))
+    GC.@preserve a check(chunk, ccall((:tl_set_field, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Clong),
+                                      chunk.ctx, FIELD_ID[field], a, size(a, 1)))
+end
+
+function download(chunk::B200Chunk, field::Symbol)::Matrix{Float64}
+    a = Matrix{Float64}(undef, chunk.x, chunk.y)
+    GC.@preserve a check(chunk, ccall((:tl_get_field, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Clong),
+                                      chunk.ctx, FIELD_ID[field], a, chunk.x))
+    return a
+end
+
+# ---- kernels, reference names (src/kernels.jl) --------------------------------------------------
+fieldmask(fields) = reduce(|, (UInt32(1) << FIELD_ID[f] for f in fields); init = UInt32(0))
+
+"haloupdate!, src/kernels.jl:146-159 (the sticky toexchange set stays in `set`)"
+function TeaLeaf.Kernels.haloupdate!(chunk::B200Chunk, set::Settings, depth::Int, toex = nothing, reset = true)
+    toex = if toex !== nothing
+        reset && resettoexchange!(set)
+        for f in toex
+            set.toexchange[f] = true
+        end
+        toex
+    else
+        filter(f -> set.toexchange[f], EXCHANGE_FIELDS)
+    end
+    isempty(toex) && return
+    check(chunk, ccall((:tl_halo_update, LIB), Cint, (Ptr{Cvoid}, Cuint, Cint), chunk.ctx, fieldmask(toex), depth))
+end
+
+"copyu!, src/kernels.jl:217-220"
+TeaLeaf.Kernels.copyu!(chunk::B200Chunk, hd::Int) = check(chunk, ccall((:tl_copy_u, LIB), Cint, (Ptr{Cvoid},), chunk.ctx))
+"residual!, src/kernels.jl:227-232"
+TeaLeaf.Kernels.residual!(chunk::B200Chunk, hd::Int) = check(chunk, ccall((:tl_calc_residual, LIB), Cint, (Ptr{Cvoid},), chunk.ctx))
+"finalise!, src/kernels.jl:239-242"
+TeaLeaf.Kernels.finalise!(chunk::B200Chunk, hd::Int) = check(chunk, ccall((:tl_finalise, LIB), Cint, (Ptr{Cvoid},), chunk.ctx))
+
+"solvefinished!, src/kernels.jl:166-170"
+function TeaLeaf.Kernels.solvefinished!(chunk::B200Chunk, set::Settings)
+    check(chunk, ccall((:tl_solve_finished, LIB), Cint, (Ptr{Cvoid}, Cint), chunk.ctx, set.checkresult))
+    set.toexchange[:energy] = true
+end
+
+"fieldsummary, src/kernels.jl:119-133 (vol, mass, ie are the upstream companions of temp)"
+function TeaLeaf.Kernels.fieldsummary(chunk::B200Chunk, set::Settings)
+    !set.checkresult && return
+    vol, mass, ie, temp = Ref(0.0), Ref(0.0), Ref(0.0), Ref(0.0)
+    check(chunk, ccall((:tl_field_summary, LIB), Cint,
+                       (Ptr{Cvoid}, Cdouble, Ref{Cdouble}, Ref{Cdouble}, Ref{Cdouble}, Ref{Cdouble}),
+                       chunk.ctx, chunk.volume, vol, mass, ie, temp))
+    actual = temp[]
+    cv = checkingvalue(set)
+    @info "Checking results..." cv actual vol[] mass[] ie[]
+    qa_diff = abs(100actual / cv - 100.0)
+    if qa_diff < 0.001
+        @info "This run PASSED" qa_diff
+    else
+        @warn "This run FAILED" qa_diff
+    end
+end
+
+# ---- solver modules: `settings.solver.solve!(chunk, settings, rx, ry)` (src/TeaLeaf.jl:74) -------
+module CG
+using ..TeaLeafB200: B200Chunk, SolveInfo, LIB, check
+using TeaLeaf
+"CG.solve!, src/solvers/CG.jl:7-29 -- one call into the fused, graph-launched device path"
+function solve!(chunk::B200Chunk, set::Settings, rx::Float64, ry::Float64)::Float64
+    info = Ref{SolveInfo}()
+    check(chunk, ccall((:tl_cg_solve, LIB), Cint,
+                       (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cdouble, Cint, Ref{SolveInfo}, Ptr{Cdouble}, Ptr{Cdouble}),
+                       chunk.ctx, set.coefficient, rx, ry, set.eps, set.maxiters, info, chunk.cgα, chunk.cgβ))
+    resettoexchange!(set); set.toexchange[:u] = true; set.toexchange[:p] = true
+    iters, error = info[].iters, info[].error
+    @info "CG solve complete" iters error
+    return error
+end
+end # module CG
+
+module Cheby
+using ..TeaLeafB200: B200Chunk, SolveInfo, LIB, check
+using TeaLeaf
+"Cheby.solve!, src/solvers/Cheby.jl:10-61"
+function solve!(chunk::B200Chunk, set::Settings, rx::Float64, ry::Float64)
+    info = Ref{SolveInfo}()
+    check(chunk, ccall((:tl_cheby_solve, LIB), Cint,
+                       (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Ref{SolveInfo}),
+                       chunk.ctx, set.coefficient, rx, ry, set.eps, set.maxiters, set.presteps, set.epslim,
+                       set.errorswitch, info))
+    resettoexchange!(set); set.toexchange[:u] = true
+    chunk.eigmin, chunk.eigmax = info[].eigmin, info[].eigmax
+    chebyiters, estiter = info[].cheby_iters, info[].est_iters
+    @info "Cheby solve complete" chebyiters estiter
+    return info[].error
+end
+end # module Cheby
+
+module PPCG
+using ..TeaLeafB200: B200Chunk, SolveInfo, LIB, check
+using TeaLeaf
+"PPCG.solve!, src/solvers/PPCG.jl:9-55"
+function solve!(chunk::B200Chunk, set::Settings, rx::Float64, ry::Float64)
+    info = Ref{SolveInfo}()
+    check(chunk, ccall((:tl_ppcg_solve, LIB), Cint,
+                       (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Cint, Ref{SolveInfo}),
+                       chunk.ctx, set.coefficient, rx, ry, set.eps, set.maxiters, set.presteps, set.epslim,
+                       set.errorswitch, set.ppcginnersteps, info))
+    resettoexchange!(set); set.toexchange[:p] = true
+    chunk.eigmin, chunk.eigmax = info[].eigmin, info[].eigmax
+    iters, error = info[].iters, info[].error
+    @info "PPCG solve complete" iters error
+    return error
+end
+end # module PPCG
+
+# ---- per-kernel entry points, for a host that keeps solve! written in Julia ---------------------
+# (same names and argument order as src/solvers/CG.jl; used by TeaLeaf.CG.mainstep! unchanged)
+function TeaLeaf.CG.init!(chunk::B200Chunk, hd::Int, coef::Int, rx::Float64, ry::Float64)
+    rro = Ref(0.0)
+    check(chunk, ccall((:tl_cg_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Ref{Cdouble}), chunk.ctx, coef, rx, ry, rro))
+    return rro[]
+end
+function TeaLeaf.CG.w!(chunk::B200Chunk, hd::Int)::Float64
+    pw = Ref(0.0)
+    check(chunk, ccall((:tl_cg_calc_w, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), chunk.ctx, pw))
+    return pw[]
+end
+function TeaLeaf.CG.ur!(chunk::B200Chunk, hd::Int, α::Float64)
+    rrn = Ref(0.0)
+    check(chunk, ccall((:tl_cg_calc_ur, LIB), Cint, (Ptr{Cvoid}, Cdouble, Ref{Cdouble}), chunk.ctx, α, rrn))
+    return rrn[]
+end
+TeaLeaf.CG.p!(chunk::B200Chunk, hd::Int, β::Float64) =
+    check(chunk, ccall((:tl_cg_calc_p, LIB), Cint, (Ptr{Cvoid}, Cdouble), chunk.ctx, β))
+
+# ---- application entry (src/TeaLeaf.jl:35-44) -----------------------------------------------------
+"""
+    initialiseapp!(settings; device = 0) -> B200Chunk
+
+`initialiseapp!` with the device chunk: the reference's own `Chunk`/`setchunkstate!` paint the
+state on the host, the painted `density`/`energy0`/`u` are uploaded once, and the rest of
+`initialiseapp!` (halo priming, `energy .= energy0`) runs on the device.
+"""
+function initialiseapp!(settings::Settings; device::Int = 0)::B200Chunk
+    host = Chunk(settings)
+    setchunkstate!(host, settings.states)
+    chunk = B200Chunk(settings; device = device)
+    upload!(chunk, :density, host.density)
+    upload!(chunk, :energy0, host.energy0)
+    upload!(chunk, :u, host.u)
+    TeaLeaf.Kernels.haloupdate!(chunk, settings, 1, [:density, :energy0, :energy])
+    check(chunk, ccall((:tl_copy_field, LIB), Cint, (Ptr{Cvoid}, Cint, Cint), chunk.ctx, FIELD_ID[:energy], FIELD_ID[:energy0]))
+    # route `set.solver.solve!` to the device modules
+    settings.solver = settings.solver === TeaLeaf.CG ? CG :
+                      settings.solver === TeaLeaf.Cheby ? Cheby :
+                      settings.solver === TeaLeaf.PPCG ? PPCG : throw("solver not available on the B200 path")
+    return chunk
+end
+
+end # module TeaLeafB200
