@@ -212,6 +212,23 @@ def run_b200(args):
     h_energy = torch.from_numpy(np.ascontiguousarray(energy0.T)).pin_memory()
     h_out = torch.empty((y, x), dtype=torch.float64).pin_memory()
 
+    # N>1: the same tile solved alone on this GPU (no neighbours, no collectives), so that the
+    # weak-scaling efficiency of THIS workload can be read from one JSON line
+    solo = None
+    if world > 1:
+        ssolo = classic(tile_nx, tile_ny, 1, maxiters=60)
+        csolo = DeviceChunk(tile_nx, tile_ny, ssolo.halodepth, ssolo.maxiters, device=local_rank)
+        csolo.set_field_raw("density", h_density.data_ptr(), x)
+        csolo.set_field_raw("energy0", h_energy.data_ptr(), x)
+        csolo.haloupdate(["density", "energy0", "energy"], 1)
+        csolo.copy_field("energy", "energy0")
+        rxs, rys = ssolo.dtinit / ssolo.dx ** 2, ssolo.dtinit / ssolo.dy ** 2
+        csolo.cg_solve(ssolo, rxs, rys)
+        csolo.timer_start()
+        isolo = csolo.cg_solve(ssolo, rxs, rys)
+        solo_ms = csolo.timer_stop()
+        solo = tile_nx * tile_ny * isolo["iters"] / (solo_ms * 1e-3)
+        csolo.close()
     chunk = DeviceChunk(tile_nx, tile_ny, s.halodepth, s.maxiters, device=local_rank, rank=rank, px=px, py=py)
     if world > 1:
         from tealeaf_jl_b200.dist import connect
@@ -341,6 +358,9 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * field_bytes,
                     "d2h_bytes_per_step": field_bytes + 32, "ms_per_step": 1e3 * e2e_wall / args.steps},
             "gpu_launches": int(launches), "clocks": clocks,
+            **({"same_tile_single_gpu": {"value": solo, "unit": UNIT, "note":
+                "this rank's tile solved alone (1x1, 60 CG iterations incl. init) in the same job; "
+                "weak-scaling efficiency of the N-GPU workload = value / (N x this)"}} if solo else {}),
         }))
     chunk.close()
     if dist is not None:

@@ -19,6 +19,7 @@
 #include "tl_device.cuh"
 #include "tl_kernels_basic.cuh"
 #include "tl_kernels_fused.cuh"
+#include "tl_kernels_ring.cuh"
 #include "tl_eigen.h"
 
 #define TL_MAX_GRID 4096
@@ -82,7 +83,9 @@ struct tl_ctx {
   cudaEvent_t ev[2]{}, ev_start = nullptr, ev_stop = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   int num_sms = 148;
   // tuning
-  int blocks_per_sm = 2, pw_blocks_per_sm = 4, chunk_rows = 0, graph_iters = 8, use_graph = 1;
+  int blocks_per_sm = 2, pw_blocks_per_sm = 4, chunk_rows = -1, pw_chunk_rows = -1, graph_iters = 8, use_graph = 1;
+  int ring_stages = -1;  // -1: auto; 0: register double-buffering; 3/4/6: cp.async shared-memory ring depth
+  int ring_eff = 0;      // the flavour in use
   double l2_persist_mb = 0.0, l2_hit_scale = 1.0;
   int l2_persist_field = TL_R;
   Tiling tiling{}, pw_tiling{};   // stencil kernels / pointwise kernels
@@ -139,8 +142,17 @@ static void make_tiling(const tl_ctx *c, int blocks_per_sm, int chunk_rows, Tili
 
 static void compute_tiling(tl_ctx *c) {
   const Geo &g = c->g;
-  make_tiling(c, c->blocks_per_sm, c->chunk_rows, &c->tiling, &c->fused_grid);
-  make_tiling(c, c->pw_blocks_per_sm, 0, &c->pw_tiling, &c->pw_grid);
+  // Measured on B200 (profiles/r01_tuning.md): short row chunks issued as several waves of
+  // memory-contiguous CTAs beat one co-resident wave; the cp.async ring wins once chunks are short.
+  // Depth 3 at 3 CTAs/SM is best up to ~4096^2 tiles, depth 4 at 2 CTAs/SM beyond.
+  const long cells_tile = (long)g.nx * g.ny;
+  c->ring_eff = c->ring_stages >= 0 ? c->ring_stages : (cells_tile >= (long)8192 * 8192 ? 4 : 3);
+  int bps = c->blocks_per_sm;
+  if (c->ring_eff) bps = (c->ring_eff == 3) ? 3 : (c->ring_eff == 4) ? 2 : 1;   // the kernels' launch bounds
+  const int cr = c->chunk_rows >= 0 ? c->chunk_rows : 8;
+  const int pcr = c->pw_chunk_rows >= 0 ? c->pw_chunk_rows : 16;
+  make_tiling(c, bps, cr, &c->tiling, &c->fused_grid);
+  make_tiling(c, c->pw_blocks_per_sm, pcr, &c->pw_tiling, &c->pw_grid);
   const long cells = (long)(g.nx + 2 * g.hd) * (g.ny + 2 * g.hd);
   long nb = (cells + TL_BASIC_THREADS - 1) / TL_BASIC_THREADS;
   c->basic_grid = (int)std::max(1L, std::min<long>(nb, (long)c->num_sms * 8));
@@ -293,10 +305,16 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   const std::string n(name);
   if (n == "blocks_per_sm") c->blocks_per_sm = std::max(1, (int)value);
   else if (n == "pw_blocks_per_sm") c->pw_blocks_per_sm = std::max(1, (int)value);
+  else if (n == "ring_stages") {
+    const int s = (int)value;
+    if (s != -1 && s != 0 && s != 3 && s != 4 && s != 6) return tl_fail(c, TL_ERR_ARG, "ring_stages must be -1, 0, 3, 4 or 6");
+    c->ring_stages = s;
+  }
   else if (n == "l2_persist_mb") c->l2_persist_mb = value;
   else if (n == "l2_hit_scale") c->l2_hit_scale = value;
   else if (n == "l2_persist_field") c->l2_persist_field = std::min(std::max(0, (int)value), (int)B_COUNT - 1);
-  else if (n == "chunk_rows") c->chunk_rows = std::max(0, (int)value);
+  else if (n == "chunk_rows") c->chunk_rows = std::max(-1, (int)value);       // -1 auto, 0 one wave
+  else if (n == "pw_chunk_rows") c->pw_chunk_rows = std::max(-1, (int)value);
   else if (n == "graph_iters") c->graph_iters = std::max(1, (int)value);
   else if (n == "use_graph") c->use_graph = value != 0.0;
   else return tl_fail(c, TL_ERR_ARG, "unknown option %s", name);
@@ -704,6 +722,79 @@ static CgBParams cg_b_params(tl_ctx *c) {
   return P;
 }
 
+// kernel A in the configured flavour (register double-buffering or cp.async ring)
+template <bool U, int S, int MINB>
+static int launch_ring(tl_ctx *c, const CgAParams &P) {
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(c, cudaFuncSetAttribute(k_cg_fused_w_ring<U, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  k_cg_fused_w_ring<U, S, MINB><<<c->fused_grid, TL_FUSED_THREADS, smem, c->stream>>>(P);
+  return TL_OK;
+}
+template <bool U>
+static int launch_cg_a(tl_ctx *c) {
+  const CgAParams P = cg_a_params(c);
+  switch (c->ring_eff) {
+    case 3: TRY((launch_ring<U, 3, 3>(c, P))); break;
+    case 4: TRY((launch_ring<U, 4, 2>(c, P))); break;
+    case 6: TRY((launch_ring<U, 6, 1>(c, P))); break;
+    default: k_cg_fused_w<U><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
+  }
+  CHECK_LAUNCH(c);
+  return TL_OK;
+}
+
+template <bool FIRST, int S, int MINB>
+static int launch_cheby_ring(tl_ctx *c, const ChebyParams &P) {
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(c, cudaFuncSetAttribute(k_cheby_fused_ring<FIRST, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  k_cheby_fused_ring<FIRST, S, MINB><<<c->fused_grid, TL_FUSED_THREADS, smem, c->stream>>>(P);
+  return TL_OK;
+}
+static ChebyParams cheby_params(tl_ctx *c);
+template <bool FIRST>
+static int launch_cheby(tl_ctx *c) {
+  const ChebyParams P = cheby_params(c);
+  switch (c->ring_eff) {
+    case 3: TRY((launch_cheby_ring<FIRST, 3, 3>(c, P))); break;
+    case 4: TRY((launch_cheby_ring<FIRST, 4, 2>(c, P))); break;
+    case 6: TRY((launch_cheby_ring<FIRST, 6, 1>(c, P))); break;
+    default: k_cheby_fused<FIRST><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
+  }
+  CHECK_LAUNCH(c);
+  return TL_OK;
+}
+template <int S, int MINB>
+static int launch_ppcg_inner_ring(tl_ctx *c, const PpcgInnerParams &P) {
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(c, cudaFuncSetAttribute(k_ppcg_inner_ring<S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  k_ppcg_inner_ring<S, MINB><<<c->fused_grid, TL_FUSED_THREADS, smem, c->stream>>>(P);
+  return TL_OK;
+}
+static PpcgInnerParams ppcg_inner_params(tl_ctx *c);
+static int launch_ppcg_inner(tl_ctx *c) {
+  const PpcgInnerParams P = ppcg_inner_params(c);
+  switch (c->ring_eff) {
+    case 3: TRY((launch_ppcg_inner_ring<3, 3>(c, P))); break;
+    case 4: TRY((launch_ppcg_inner_ring<4, 2>(c, P))); break;
+    case 6: TRY((launch_ppcg_inner_ring<6, 1>(c, P))); break;
+    default: k_ppcg_inner<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
+  }
+  CHECK_LAUNCH(c);
+  return TL_OK;
+}
+
 // One CG iteration on the stream: [halo pulls of r, p when tiled] A, allreduce(pw), B, allreduce(rr).
 static int enqueue_cg_iteration(tl_ctx *c) {
   if (c->nranks > 1) {
@@ -712,8 +803,7 @@ static int enqueue_cg_iteration(tl_ctx *c) {
     TRY(pull_halo(c, TL_P, 1));
     TRY(pull_halo(c, B_P1, 1));
   }
-  k_cg_fused_w<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
-  CHECK_LAUNCH(c);
+  TRY(launch_cg_a<true>(c));
   if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
   k_cg_fused_r<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
   CHECK_LAUNCH(c);
@@ -876,8 +966,7 @@ static int enqueue_cheby_iteration(tl_ctx *c) {
     TRY(pull_halo(c, TL_U, 1));
     TRY(pull_halo(c, B_U1, 1));
   }
-  k_cheby_fused<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cheby_params(c));
-  CHECK_LAUNCH(c);
+  TRY(launch_cheby<false>(c));
   if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_norm_local, &c->st->red_norm, 1));
   c->launches++;
   return TL_OK;
@@ -934,9 +1023,8 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
   // both u buffers must agree outside the cells the fused kernel writes
   LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[TL_U], c->buf[B_U1]);
   // Cheby.init! field part + bb
-  k_cheby_fused<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cheby_params(c));
+  TRY(launch_cheby<true>(c));
   c->launches++;
-  CHECK_LAUNCH(c);
   if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_norm_local, &c->st->red_norm, 1));
   double bb = 0.0, error = 0.0;
   TRY(read_scalars(c, &c->st->red_norm, 1, &bb));
@@ -991,8 +1079,7 @@ static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps) {
     TRY(pull_halo(c, TL_P, 1));
     TRY(pull_halo(c, B_P1, 1));
   }
-  k_cg_fused_w<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
-  CHECK_LAUNCH(c);
+  TRY(launch_cg_a<false>(c));
   if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
   k_ppcg_ur_sd<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_ur_params(c));
   CHECK_LAUNCH(c);
@@ -1002,8 +1089,7 @@ static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps) {
       TRY(pull_halo(c, TL_SD, 1));
       TRY(pull_halo(c, B_SD1, 1));
     }
-    k_ppcg_inner<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_inner_params(c));
-    CHECK_LAUNCH(c);
+    TRY(launch_ppcg_inner(c));
   }
   if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
   c->launches += 2 + inner_steps;
@@ -1091,11 +1177,11 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
   k_state_for_timing<<<1, 1, 0, c->stream>>>(c->st, c->hist_rr, c->hist_pw, c->ch_alphas, c->ch_betas, c->max_iters);
   CHECK_LAUNCH(c);
   auto launch = [&]() -> int {
-    if (k == "cg_fused_w") k_cg_fused_w<true><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
-    else if (k == "cg_fused_w_nou") k_cg_fused_w<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_a_params(c));
+    if (k == "cg_fused_w") TRY(launch_cg_a<true>(c));
+    else if (k == "cg_fused_w_nou") TRY(launch_cg_a<false>(c));
     else if (k == "cg_fused_r") k_cg_fused_r<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
-    else if (k == "cheby_fused") k_cheby_fused<false><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(cheby_params(c));
-    else if (k == "ppcg_inner") k_ppcg_inner<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_inner_params(c));
+    else if (k == "cheby_fused") TRY(launch_cheby<false>(c));
+    else if (k == "ppcg_inner") TRY(launch_ppcg_inner(c));
     else return tl_fail(c, TL_ERR_ARG, "tl_time_kernel: unknown kernel %s", kernel);
     c->launches++;
     return TL_OK;

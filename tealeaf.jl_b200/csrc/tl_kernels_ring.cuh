@@ -1,0 +1,455 @@
+// tl_kernels_ring.cuh -- shared-memory ring variants of the stencil kernels.
+//
+// Same warp-strip marching as tl_kernels_fused.cuh, but the loads for the next S-1 rows are in
+// flight as asynchronous global->shared copies (cp.async / LDGSTS, 16 B per lane) instead of
+// sitting in registers: every warp owns a private ring of S row-slots in shared memory, each lane
+// reads back only the bytes it copied itself, so no barrier of any kind is needed -- completion
+// is tracked per thread with cp.async commit/wait groups.  The memory system then sees
+// (S-1) x 2.5 KB per warp in flight (vs 2.5 KB with register double-buffering), which is what an
+// HBM3e stack at ~1 us loaded latency needs (Little: 6.5 TB/s x 1 us = 6.5 MB chip-wide).
+#pragma once
+#include "tl_kernels_fused.cuh"
+
+#define TL_RING_FIELDS 5
+#define TL_RING_STAGE_BYTES (TL_RING_FIELDS * 512 + 64)   // 5 x (32 lanes x 16 B) + edge scalars
+
+__device__ __forceinline__ unsigned tl_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tl_cp16(unsigned dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tl_cp8(unsigned dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tl_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tl_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ double2 tl_lds2(unsigned a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double tl_lds1(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+
+// CG kernel A, ring variant (see k_cg_fused_w for the algorithm and the citations).
+template <bool UPDATE_U, int S, int MINB>
+__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(const CgAParams P) {
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  __shared__ double sm[32];
+  SolveState *st = P.st;
+  const int it = st->iter;
+  const double rr_cur = st->red_rr;
+  if (tl_should_stop(it, rr_cur, st->cfg)) return;
+  const bool first = (it == st->cfg.first_it);
+  double beta = 0.0, alpha_prev = 0.0;
+  if (!first) {
+    const double rr_prev = P.hist_rr[it - 1];
+    beta = rr_cur / rr_prev;
+    alpha_prev = rr_prev / P.hist_pw[it];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_rr[it] = rr_cur;
+  const double *__restrict__ pin = (it & 1) ? P.p1 : P.p0;
+  double *__restrict__ pout = (it & 1) ? P.p0 : P.p1;
+  const double *__restrict__ r = P.r;
+  const double *__restrict__ kx = P.kx;
+  const double *__restrict__ ky = P.ky;
+  double *__restrict__ u = P.u;
+  double *__restrict__ w = P.w;
+  const Geo g = P.g;
+  const int pitch = g.pitch;
+  const bool physL = g.phys & TL_PHYS_LEFT, physR = g.phys & TL_PHYS_RIGHT;
+  const bool physB = g.phys & TL_PHYS_BOTTOM, physT = g.phys & TL_PHYS_TOP;
+
+  double acc[1] = {0.0};
+  MarchCtx m;
+  if (tl_march_setup(g, P.t, m)) {
+    const double2 z2 = make_double2(0.0, 0.0);
+    auto comb = [&](double rv, double pv) { return first ? pv : beta * pv + rv; };
+    auto comb2 = [&](double2 rv, double2 pv) { return make_double2(comb(rv.x, pv.x), comb(rv.y, pv.y)); };
+    // this warp's ring; slot layout: [field 0..4][lane] double2, then 8 edge doubles
+    const unsigned ring = tl_smem_u32(ring_raw) + (threadIdx.x >> 5) * (S * TL_RING_STAGE_BYTES);
+    const unsigned lane_off = m.lane * 16;
+    const unsigned edge_off = TL_RING_FIELDS * 512 + (m.lane == 0 ? 0 : 24);   // lane 0: 3 doubles, lane 31: 3 doubles
+    auto issue = [&](int j, int stage) {
+      const unsigned base = ring + stage * TL_RING_STAGE_BYTES;
+      const int jn = (j + 1 >= g.ny && physT) ? g.ny - 1 : j + 1;
+      const long on = (long)jn * pitch + m.i0, oc = (long)j * pitch + m.i0;
+      if (m.ld_ok) {
+        tl_cp16(base + 0 * 512 + lane_off, r + on);
+        tl_cp16(base + 1 * 512 + lane_off, pin + on);
+        tl_cp16(base + 2 * 512 + lane_off, ky + oc + pitch);
+        tl_cp16(base + 3 * 512 + lane_off, kx + oc);
+      }
+      if (UPDATE_U && m.acta) tl_cp16(base + 4 * 512 + lane_off, u + oc);
+      if (m.has_edge) {
+        const long oe = (long)jn * pitch + m.ecol;
+        tl_cp8(base + edge_off + 0, r + oe);
+        tl_cp8(base + edge_off + 8, pin + oe);
+        if (m.lane == 31) tl_cp8(base + edge_off + 16, kx + (long)j * pitch + m.ecol);
+      }
+    };
+    // prologue: rows j0-1 (clamped on a physical bottom) and j0, plain loads
+    double2 Xm, Xc, pc, kyc;
+    double XcE;
+    {
+      const int jm = (m.j0 == 0 && physB) ? 0 : m.j0 - 1;
+      const long om = (long)jm * pitch + m.i0, oc = (long)m.j0 * pitch + m.i0;
+      const double2 rm = m.ld_ok ? tl_ld2(r + om) : z2, pm = m.ld_ok ? tl_ld2(pin + om) : z2;
+      const double2 rc = m.ld_ok ? tl_ld2(r + oc) : z2;
+      pc = m.ld_ok ? tl_ld2(pin + oc) : z2;
+      kyc = m.ld_ok ? tl_ld2(ky + oc) : z2;
+      const long oe = (long)m.j0 * pitch + m.ecol;
+      const double re = m.has_edge ? __ldg(r + oe) : 0.0, pe = m.has_edge ? __ldg(pin + oe) : 0.0;
+      Xm = comb2(rm, pm);
+      Xc = comb2(rc, pc);
+      XcE = comb(re, pe);
+    }
+#pragma unroll
+    for (int d = 0; d < S - 1; d++) {
+      if (m.j0 + d < m.j1) issue(m.j0 + d, d);
+      tl_cp_commit();
+    }
+    int stage = 0;            // slot holding row j
+    int fill = S - 1;         // slot that receives row j + S - 1
+    for (int j = m.j0; j < m.j1; j++) {
+      if (j + S - 1 < m.j1) issue(j + S - 1, fill);
+      tl_cp_commit();
+      tl_cp_wait<S - 1>();
+      const unsigned base = ring + stage * TL_RING_STAGE_BYTES;
+      const double2 c_r = m.ld_ok ? tl_lds2(base + 0 * 512 + lane_off) : z2;
+      const double2 c_p = m.ld_ok ? tl_lds2(base + 1 * 512 + lane_off) : z2;
+      const double2 c_ky = m.ld_ok ? tl_lds2(base + 2 * 512 + lane_off) : z2;
+      const double2 c_kx = m.ld_ok ? tl_lds2(base + 3 * 512 + lane_off) : z2;
+      const double2 c_u = (UPDATE_U && m.acta) ? tl_lds2(base + 4 * 512 + lane_off) : z2;
+      const double c_re = m.has_edge ? tl_lds1(base + edge_off + 0) : 0.0;
+      const double c_pe = m.has_edge ? tl_lds1(base + edge_off + 8) : 0.0;
+      const double c_kxe = (m.lane == 31 && m.has_edge) ? tl_lds1(base + edge_off + 16) : 0.0;
+      stage = (stage + 1 == S) ? 0 : stage + 1;
+      fill = (fill + 1 == S) ? 0 : fill + 1;
+
+      const double2 Xn = comb2(c_r, c_p);
+      const double XnE = comb(c_re, c_pe);
+      double xl = __shfl_up_sync(0xffffffffu, Xc.y, 1);
+      double xr = __shfl_down_sync(0xffffffffu, Xc.x, 1);
+      double kxr = __shfl_down_sync(0xffffffffu, c_kx.x, 1);
+      if (m.lane == 0) xl = XcE;
+      if (m.lane == 31) { xr = XcE; kxr = c_kxe; }
+      const double La = (physL && m.i0 == 0) ? Xc.x : xl;
+      const double Ra = (physR && m.i0 == g.nx - 1) ? Xc.x : Xc.y;
+      const double Lb = Xc.x;
+      const double Rb = (physR && m.i0 + 1 == g.nx - 1) ? Xc.y : xr;
+      const double wa = ((((1.0 + c_kx.y) + c_kx.x) + c_ky.x) + kyc.x) * Xc.x -
+                        (c_kx.y * Ra + c_kx.x * La) - (c_ky.x * Xn.x + kyc.x * Xm.x);
+      const double wb = ((((1.0 + kxr) + c_kx.y) + c_ky.y) + kyc.y) * Xc.y -
+                        (kxr * Rb + c_kx.y * Lb) - (c_ky.y * Xn.y + kyc.y * Xm.y);
+      const long oc = (long)j * pitch + m.i0;
+      double2 un = z2;
+      if (UPDATE_U) un = make_double2(c_u.x + alpha_prev * pc.x, c_u.y + alpha_prev * pc.y);
+      if (m.actb) {
+        tl_st2(w + oc, make_double2(wa, wb));
+        tl_st2(pout + oc, Xc);
+        if (UPDATE_U) tl_st2(u + oc, un);
+        acc[0] += wa * Xc.x;
+        acc[0] += wb * Xc.y;
+      } else if (m.acta) {
+        w[oc] = wa; pout[oc] = Xc.x;
+        if (UPDATE_U) u[oc] = un.x;
+        acc[0] += wa * Xc.x;
+      }
+      if (m.acta) {
+        if (physL && m.i0 == 0) { pout[oc - 1] = Xc.x; if (UPDATE_U) u[oc - 1] = un.x; }
+        if (physR && m.i0 == g.nx - 1) { pout[oc + 1] = Xc.x; if (UPDATE_U) u[oc + 1] = un.x; }
+        if (physR && m.i0 + 1 == g.nx - 1) { pout[oc + 2] = Xc.y; if (UPDATE_U) u[oc + 2] = un.y; }
+        if (physB && j == 0) {
+          pout[oc - pitch] = Xc.x; if (UPDATE_U) u[oc - pitch] = un.x;
+          if (m.actb) { pout[oc - pitch + 1] = Xc.y; if (UPDATE_U) u[oc - pitch + 1] = un.y; }
+        }
+        if (physT && j == g.ny - 1) {
+          pout[oc + pitch] = Xc.x; if (UPDATE_U) u[oc + pitch] = un.x;
+          if (m.actb) { pout[oc + pitch + 1] = Xc.y; if (UPDATE_U) u[oc + pitch + 1] = un.y; }
+        }
+      }
+      Xm = Xc; Xc = Xn; XcE = XnE; pc = c_p; kyc = c_ky;
+    }
+    tl_cp_wait<0>();
+  }
+  if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) {
+    st->red_pw_local = acc[0];
+    if (P.single) st->red_pw = acc[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared pieces of the single-operand stencil kernels (Chebyshev: operand u; PPCG inner: sd).
+// Ring slot: field 0 = operand at row jn, 1 = ky(j+1), 2 = kx(j), 3/4 = two pointwise fields
+// at row j; edges: operand at (ecol, jn), kx at (ecol, j) for lane 31.
+// ------------------------------------------------------------------------------------------
+struct RingRow {
+  double2 x, ky, kx, a, b;
+  double xe, kxe;
+};
+
+template <int S>
+struct RingMarch {
+  unsigned ring, lane_off, edge_off;
+  int stage, fill;
+  __device__ __forceinline__ void init(const unsigned char *raw, const MarchCtx &m) {
+    ring = tl_smem_u32(raw) + (threadIdx.x >> 5) * (S * TL_RING_STAGE_BYTES);
+    lane_off = m.lane * 16;
+    edge_off = TL_RING_FIELDS * 512 + (m.lane == 0 ? 0 : 24);
+    stage = 0;
+    fill = S - 1;
+  }
+  // fa / fb may be null (field not needed)
+  __device__ __forceinline__ void issue(const Geo &g, const MarchCtx &m, bool physT, int j, int slot,
+                                        const double *x, const double *ky, const double *kx, const double *fa,
+                                        const double *fb) const {
+    const unsigned base = ring + slot * TL_RING_STAGE_BYTES;
+    const int jn = (j + 1 >= g.ny && physT) ? g.ny - 1 : j + 1;
+    const long on = (long)jn * g.pitch + m.i0, oc = (long)j * g.pitch + m.i0;
+    if (m.ld_ok) {
+      tl_cp16(base + 0 * 512 + lane_off, x + on);
+      tl_cp16(base + 1 * 512 + lane_off, ky + oc + g.pitch);
+      tl_cp16(base + 2 * 512 + lane_off, kx + oc);
+    }
+    if (m.acta) {
+      if (fa) tl_cp16(base + 3 * 512 + lane_off, fa + oc);
+      if (fb) tl_cp16(base + 4 * 512 + lane_off, fb + oc);
+    }
+    if (m.has_edge) {
+      tl_cp8(base + edge_off + 0, x + (long)jn * g.pitch + m.ecol);
+      if (m.lane == 31) tl_cp8(base + edge_off + 8, kx + (long)j * g.pitch + m.ecol);
+    }
+  }
+  __device__ __forceinline__ RingRow take(const MarchCtx &m, bool has_a, bool has_b) {
+    const double2 z2 = make_double2(0.0, 0.0);
+    const unsigned base = ring + stage * TL_RING_STAGE_BYTES;
+    RingRow r;
+    r.x = m.ld_ok ? tl_lds2(base + 0 * 512 + lane_off) : z2;
+    r.ky = m.ld_ok ? tl_lds2(base + 1 * 512 + lane_off) : z2;
+    r.kx = m.ld_ok ? tl_lds2(base + 2 * 512 + lane_off) : z2;
+    r.a = (has_a && m.acta) ? tl_lds2(base + 3 * 512 + lane_off) : z2;
+    r.b = (has_b && m.acta) ? tl_lds2(base + 4 * 512 + lane_off) : z2;
+    r.xe = m.has_edge ? tl_lds1(base + edge_off + 0) : 0.0;
+    r.kxe = (m.lane == 31 && m.has_edge) ? tl_lds1(base + edge_off + 8) : 0.0;
+    stage = (stage + 1 == S) ? 0 : stage + 1;
+    fill = (fill + 1 == S) ? 0 : fill + 1;
+    return r;
+  }
+};
+
+// w = A x at this lane's two cells (same expression order as tl_smvp / the oracle)
+__device__ __forceinline__ void tl_stencil2(const Geo &g, const MarchCtx &m, bool physL, bool physR, double2 Xm,
+                                            double2 Xc, double2 Xn, double XcE, double2 kxv, double kxe, double2 kyc,
+                                            double2 kyn, double &wa, double &wb) {
+  double xl = __shfl_up_sync(0xffffffffu, Xc.y, 1);
+  double xr = __shfl_down_sync(0xffffffffu, Xc.x, 1);
+  double kxr = __shfl_down_sync(0xffffffffu, kxv.x, 1);
+  if (m.lane == 0) xl = XcE;
+  if (m.lane == 31) { xr = XcE; kxr = kxe; }
+  const double La = (physL && m.i0 == 0) ? Xc.x : xl;
+  const double Ra = (physR && m.i0 == g.nx - 1) ? Xc.x : Xc.y;
+  const double Lb = Xc.x;
+  const double Rb = (physR && m.i0 + 1 == g.nx - 1) ? Xc.y : xr;
+  wa = ((((1.0 + kxv.y) + kxv.x) + kyn.x) + kyc.x) * Xc.x - (kxv.y * Ra + kxv.x * La) - (kyn.x * Xn.x + kyc.x * Xm.x);
+  wb = ((((1.0 + kxr) + kxv.y) + kyn.y) + kyc.y) * Xc.y - (kxr * Rb + kxv.y * Lb) - (kyn.y * Xn.y + kyc.y * Xm.y);
+}
+
+// Chebyshev iteration, ring variant (see k_cheby_fused).
+template <bool FIRST, int S, int MINB>
+__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(const ChebyParams P) {
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  __shared__ double sm[32];
+  SolveState *st = P.st;
+  const int step = st->cheby_step;
+  double alpha = 0.0, beta = 0.0;
+  bool calc_norm, store_wr;
+  const double theta = st->theta;
+  if (FIRST) {
+    calc_norm = true;
+    store_wr = true;
+  } else {
+    if (tl_cheby_should_stop(*st)) return;
+    const int chebyiters = step;
+    const int tt = st->cheby_tt0 + chebyiters - 1;
+    alpha = P.alphas[chebyiters];
+    beta = P.betas[chebyiters];
+    calc_norm = tl_cheby_is_norm_iter(chebyiters, st->cheby_tt0, st->cheby_est);
+    store_wr = calc_norm || (tt == st->cheby_max_tt);
+  }
+  const double *__restrict__ uin = (step & 1) ? P.ub : P.ua;
+  double *__restrict__ uout = (step & 1) ? P.ua : P.ub;
+  const double *__restrict__ u0 = P.u0;
+  const double *__restrict__ kx = P.kx;
+  const double *__restrict__ ky = P.ky;
+  double *__restrict__ p = P.p;
+  const Geo g = P.g;
+  const int pitch = g.pitch;
+  const bool physL = g.phys & TL_PHYS_LEFT, physR = g.phys & TL_PHYS_RIGHT;
+  const bool physB = g.phys & TL_PHYS_BOTTOM, physT = g.phys & TL_PHYS_TOP;
+
+  double acc[1] = {0.0};
+  MarchCtx m;
+  if (tl_march_setup(g, P.t, m)) {
+    const double2 z2 = make_double2(0.0, 0.0);
+    RingMarch<S> rg;
+    rg.init(ring_raw, m);
+    double2 Xm, Xc, kyc;
+    double XcE;
+    {
+      const int jm = (m.j0 == 0 && physB) ? 0 : m.j0 - 1;
+      const long om = (long)jm * pitch + m.i0, oc = (long)m.j0 * pitch + m.i0;
+      Xm = m.ld_ok ? tl_ld2(uin + om) : z2;
+      Xc = m.ld_ok ? tl_ld2(uin + oc) : z2;
+      kyc = m.ld_ok ? tl_ld2(ky + oc) : z2;
+      XcE = m.has_edge ? __ldg(uin + (long)m.j0 * pitch + m.ecol) : 0.0;
+    }
+#pragma unroll
+    for (int d = 0; d < S - 1; d++) {
+      if (m.j0 + d < m.j1) rg.issue(g, m, physT, m.j0 + d, d, uin, ky, kx, u0, FIRST ? nullptr : p);
+      tl_cp_commit();
+    }
+    for (int j = m.j0; j < m.j1; j++) {
+      if (j + S - 1 < m.j1) rg.issue(g, m, physT, j + S - 1, rg.fill, uin, ky, kx, u0, FIRST ? nullptr : p);
+      tl_cp_commit();
+      tl_cp_wait<S - 1>();
+      const RingRow cur = rg.take(m, true, !FIRST);
+      const double2 Xn = cur.x;
+      double wa, wb;
+      tl_stencil2(g, m, physL, physR, Xm, Xc, Xn, XcE, cur.kx, cur.kxe, kyc, cur.ky, wa, wb);
+      const double ra = cur.a.x - wa, rb = cur.a.y - wb;
+      double2 pn;
+      if (FIRST) { pn.x = ra / theta; pn.y = rb / theta; }
+      else { pn.x = alpha * cur.b.x + beta * ra; pn.y = alpha * cur.b.y + beta * rb; }
+      const double2 un = make_double2(Xc.x + pn.x, Xc.y + pn.y);
+      const long oc = (long)j * pitch + m.i0;
+      if (m.actb) {
+        tl_st2(p + oc, pn);
+        tl_st2(uout + oc, un);
+        if (store_wr) { tl_st2(P.w + oc, make_double2(wa, wb)); tl_st2(P.r + oc, make_double2(ra, rb)); }
+        if (FIRST) { acc[0] += cur.a.x * cur.a.x; acc[0] += cur.a.y * cur.a.y; }
+        else { acc[0] += ra * ra; acc[0] += rb * rb; }
+      } else if (m.acta) {
+        p[oc] = pn.x; uout[oc] = un.x;
+        if (store_wr) { P.w[oc] = wa; P.r[oc] = ra; }
+        acc[0] += FIRST ? cur.a.x * cur.a.x : ra * ra;
+      }
+      if (m.acta) {
+        if (physL && m.i0 == 0) uout[oc - 1] = un.x;
+        if (physR && m.i0 == g.nx - 1) uout[oc + 1] = un.x;
+        if (physR && m.i0 + 1 == g.nx - 1) uout[oc + 2] = un.y;
+        if (physB && j == 0) { uout[oc - pitch] = un.x; if (m.actb) uout[oc - pitch + 1] = un.y; }
+        if (physT && j == g.ny - 1) { uout[oc + pitch] = un.x; if (m.actb) uout[oc + pitch + 1] = un.y; }
+      }
+      Xm = Xc; Xc = Xn; XcE = cur.xe; kyc = cur.ky;
+    }
+    tl_cp_wait<0>();
+  }
+  if (calc_norm) {
+    if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) {
+      st->red_norm_local = acc[0];
+      if (P.single) st->red_norm = acc[0];
+      st->cheby_step = step + 1;
+    }
+  } else {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&st->counter, 1u) == gridDim.x - 1) { st->counter = 0u; st->cheby_step = step + 1; }
+    }
+  }
+}
+
+// PPCG inner step, ring variant (see k_ppcg_inner).
+template <int S, int MINB>
+__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(const PpcgInnerParams P) {
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  __shared__ double sm[32];
+  SolveState *st = P.st;
+  const int it = st->iter;
+  if (tl_should_stop(it, st->red_rr, st->cfg)) return;
+  const int pp = st->inner_pp;
+  const bool last = (pp + 1 == st->inner_steps);
+  const double alpha = P.alphas[pp], beta = P.betas[pp];
+  const double *__restrict__ sin = (pp & 1) ? P.sdb : P.sda;
+  double *__restrict__ sout = (pp & 1) ? P.sda : P.sdb;
+  const double *__restrict__ kx = P.kx;
+  const double *__restrict__ ky = P.ky;
+  double *__restrict__ r = P.r;
+  double *__restrict__ u = P.u;
+  const Geo g = P.g;
+  const int pitch = g.pitch;
+  const bool physL = g.phys & TL_PHYS_LEFT, physR = g.phys & TL_PHYS_RIGHT;
+  const bool physB = g.phys & TL_PHYS_BOTTOM, physT = g.phys & TL_PHYS_TOP;
+
+  double acc[1] = {0.0};
+  MarchCtx m;
+  if (tl_march_setup(g, P.t, m)) {
+    const double2 z2 = make_double2(0.0, 0.0);
+    RingMarch<S> rg;
+    rg.init(ring_raw, m);
+    double2 Xm, Xc, kyc;
+    double XcE;
+    {
+      const int jm = (m.j0 == 0 && physB) ? 0 : m.j0 - 1;
+      const long om = (long)jm * pitch + m.i0, oc = (long)m.j0 * pitch + m.i0;
+      Xm = m.ld_ok ? tl_ld2(sin + om) : z2;
+      Xc = m.ld_ok ? tl_ld2(sin + oc) : z2;
+      kyc = m.ld_ok ? tl_ld2(ky + oc) : z2;
+      XcE = m.has_edge ? __ldg(sin + (long)m.j0 * pitch + m.ecol) : 0.0;
+    }
+#pragma unroll
+    for (int d = 0; d < S - 1; d++) {
+      if (m.j0 + d < m.j1) rg.issue(g, m, physT, m.j0 + d, d, sin, ky, kx, r, u);
+      tl_cp_commit();
+    }
+    for (int j = m.j0; j < m.j1; j++) {
+      if (j + S - 1 < m.j1) rg.issue(g, m, physT, j + S - 1, rg.fill, sin, ky, kx, r, u);
+      tl_cp_commit();
+      tl_cp_wait<S - 1>();
+      const RingRow cur = rg.take(m, true, true);
+      const double2 Xn = cur.x;
+      double wa, wb;
+      tl_stencil2(g, m, physL, physR, Xm, Xc, Xn, XcE, cur.kx, cur.kxe, kyc, cur.ky, wa, wb);
+      const double2 rn = make_double2(cur.a.x - wa, cur.a.y - wb);
+      const double2 un = make_double2(cur.b.x + Xc.x, cur.b.y + Xc.y);
+      const double2 sn = make_double2(alpha * Xc.x + beta * rn.x, alpha * Xc.y + beta * rn.y);
+      const long oc = (long)j * pitch + m.i0;
+      if (m.actb) {
+        tl_st2(r + oc, rn); tl_st2(u + oc, un); tl_st2(sout + oc, sn);
+        acc[0] += rn.x * rn.x;
+        acc[0] += rn.y * rn.y;
+      } else if (m.acta) {
+        r[oc] = rn.x; u[oc] = un.x; sout[oc] = sn.x;
+        acc[0] += rn.x * rn.x;
+      }
+      if (m.acta) {
+        const double ha = last ? Xc.x : sn.x, hb = last ? Xc.y : sn.y;
+        if (physL && m.i0 == 0) sout[oc - 1] = ha;
+        if (physR && m.i0 == g.nx - 1) sout[oc + 1] = ha;
+        if (physR && m.i0 + 1 == g.nx - 1) sout[oc + 2] = hb;
+        if (physB && j == 0) { sout[oc - pitch] = ha; if (m.actb) sout[oc - pitch + 1] = hb; }
+        if (physT && j == g.ny - 1) { sout[oc + pitch] = ha; if (m.actb) sout[oc + pitch + 1] = hb; }
+      }
+      Xm = Xc; Xc = Xn; XcE = cur.xe; kyc = cur.ky;
+    }
+    tl_cp_wait<0>();
+  }
+  if (last) {
+    if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) {
+      st->red_rr_local = acc[0];
+      if (P.single) st->red_rr = acc[0];
+      st->iter = it + 1;
+      st->inner_pp = pp + 1;
+    }
+  } else {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&st->counter, 1u) == gridDim.x - 1) { st->counter = 0u; st->inner_pp = pp + 1; }
+    }
+  }
+}
