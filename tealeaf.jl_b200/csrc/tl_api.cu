@@ -63,6 +63,7 @@ struct CommBlob {  // what tl_comm_export hands to the other ranks
   cudaIpcMemHandle_t handle;
   int nx, ny, hd, pitch;
   long long buf_offset[B_COUNT];  // byte offset of interior cell (0,0) of each buffer in the slab
+  long long mail_offset;          // byte offset of the tile's mailbox (tl_tile_exchange)
   int rank, device;
 };
 
@@ -84,8 +85,9 @@ struct tl_ctx {
   int num_sms = 148;
   // tuning
   int blocks_per_sm = 2, pw_blocks_per_sm = 4, chunk_rows = -1, pw_chunk_rows = -1, graph_iters = 8, use_graph = 1;
-  int ring_stages = -1;  // -1: auto; 0: register double-buffering; 3/4/6: cp.async shared-memory ring depth
+  int ring_stages = -1;  // -1: auto; 3/4/6: cp.async shared-memory ring depth
   int ring_eff = 0;      // the flavour in use
+  int hint_keep = TL_HINT_NORMAL, hint_stream = TL_HINT_NORMAL, b_reverse = 1;   // L2 reuse between CG kernels A and B
   double l2_persist_mb = 0.0, l2_hit_scale = 1.0;
   int l2_persist_field = TL_R;
   Tiling tiling{}, pw_tiling{};   // stencil kernels / pointwise kernels
@@ -97,7 +99,11 @@ struct tl_ctx {
   int nbr_rank[4] = {-1, -1, -1, -1};
   void *peer_slab[4]{};
   CommBlob peer_blob[4]{};
+  void *rank_slab[TL_MAX_RANKS]{};   // every other tile's slab, CUDA-IPC mapped (mailboxes; the neighbours' fields)
   bool comm_ready = false;
+  int comm_fused = 1;       // 1: halo pushes + mailbox allreduce inside the kernels; 0: halo-pull kernels + NCCL
+  CommDev *d_comm = nullptr;   // device copy of the mailbox table (in the slab)
+  MailSlot *mail = nullptr;
 #ifdef TL_WITH_NCCL
   ncclComm_t nccl = nullptr;
 #endif
@@ -147,8 +153,7 @@ static void compute_tiling(tl_ctx *c) {
   // Depth 3 at 3 CTAs/SM is best up to ~4096^2 tiles, depth 4 at 2 CTAs/SM beyond.
   const long cells_tile = (long)g.nx * g.ny;
   c->ring_eff = c->ring_stages >= 0 ? c->ring_stages : (cells_tile >= (long)8192 * 8192 ? 4 : 3);
-  int bps = c->blocks_per_sm;
-  if (c->ring_eff) bps = (c->ring_eff == 3) ? 3 : (c->ring_eff == 4) ? 2 : 1;   // the kernels' launch bounds
+  const int bps = (c->ring_eff == 3) ? 3 : (c->ring_eff == 4) ? 2 : 1;   // the kernels' launch bounds
   const int cr = c->chunk_rows >= 0 ? c->chunk_rows : 8;
   const int pcr = c->pw_chunk_rows >= 0 ? c->pw_chunk_rows : 16;
   make_tiling(c, bps, cr, &c->tiling, &c->fused_grid);
@@ -206,7 +211,7 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
   if (!out) return TL_ERR_ARG;
   *out = nullptr;
   if (xcells < 1 || ycells < 1 || halo_depth < 1 || halo_depth > TL_XPAD || max_iters < 1 || px < 1 || py < 1 ||
-      rank < 0 || rank >= px * py)
+      rank < 0 || rank >= px * py || px * py > TL_MAX_RANKS)
     return TL_ERR_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device >= ndev) {
@@ -240,6 +245,8 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
   const size_t off_state = bytes; bytes += 4096;
   const size_t off_hist = bytes; bytes += 4 * hist * sizeof(double);
   const size_t off_part = bytes; bytes += 4 * TL_MAX_GRID * sizeof(double);
+  const size_t off_mail = bytes; bytes += 2 * TL_MAX_RANKS * sizeof(MailSlot);
+  const size_t off_comm = bytes; bytes += (sizeof(CommDev) + 255) / 256 * 256;
   c->slab_bytes = bytes;
   cudaError_t e = cudaMalloc((void **)&c->slab, bytes);
   if (e != cudaSuccess) {
@@ -256,6 +263,8 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
   c->ch_alphas = c->hist_pw + hist;
   c->ch_betas = c->ch_alphas + hist;
   c->partials = (double *)(c->slab + off_part);
+  c->mail = (MailSlot *)(c->slab + off_mail);
+  c->d_comm = (CommDev *)(c->slab + off_comm);
   if (cudaMallocHost((void **)&c->h_st, 2 * sizeof(SolveState)) != cudaSuccess ||
       cudaMallocHost((void **)&c->h_scal, 64 * sizeof(double)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -285,8 +294,8 @@ extern "C" void tl_destroy(tl_ctx *c) {
 #ifdef TL_WITH_NCCL
   if (c->nccl && nccl_api().ok) nccl_api().CommDestroy(c->nccl);
 #endif
-  for (int s = 0; s < 4; s++)
-    if (c->peer_slab[s]) cudaIpcCloseMemHandle(c->peer_slab[s]);
+  for (int r = 0; r < TL_MAX_RANKS; r++)
+    if (c->rank_slab[r]) cudaIpcCloseMemHandle(c->rank_slab[r]);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
   if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -307,9 +316,13 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "pw_blocks_per_sm") c->pw_blocks_per_sm = std::max(1, (int)value);
   else if (n == "ring_stages") {
     const int s = (int)value;
-    if (s != -1 && s != 0 && s != 3 && s != 4 && s != 6) return tl_fail(c, TL_ERR_ARG, "ring_stages must be -1, 0, 3, 4 or 6");
+    if (s != -1 && s != 3 && s != 4 && s != 6) return tl_fail(c, TL_ERR_ARG, "ring_stages must be -1, 3, 4 or 6");
     c->ring_stages = s;
   }
+  else if (n == "hint_keep") c->hint_keep = std::min(std::max(0, (int)value), 2);
+  else if (n == "hint_stream") c->hint_stream = std::min(std::max(0, (int)value), 2);
+  else if (n == "b_reverse") c->b_reverse = value != 0.0;
+  else if (n == "comm_fused") c->comm_fused = value != 0.0;
   else if (n == "l2_persist_mb") c->l2_persist_mb = value;
   else if (n == "l2_hit_scale") c->l2_hit_scale = value;
   else if (n == "l2_persist_field") c->l2_persist_field = std::min(std::max(0, (int)value), (int)B_COUNT - 1);
@@ -338,6 +351,7 @@ extern "C" int tl_comm_export(tl_ctx *c, void *blob) {
   CU(c, cudaIpcGetMemHandle(&b.handle, c->slab));
   b.nx = c->g.nx; b.ny = c->g.ny; b.hd = c->g.hd; b.pitch = c->g.pitch;
   for (int i = 0; i < B_COUNT; i++) b.buf_offset[i] = (long long)((char *)c->buf[i] - c->slab);
+  b.mail_offset = (long long)((char *)c->mail - c->slab);
   b.rank = c->rank; b.device = c->device;
   memcpy(blob, &b, sizeof b);
   return TL_OK;
@@ -362,11 +376,23 @@ extern "C" int tl_comm_connect(tl_ctx *c, const void *all_blobs, const void *id1
   if (!all_blobs || !id128) return tl_fail(c, TL_ERR_ARG, "tl_comm_connect: blobs and NCCL id are required");
   CU(c, cudaSetDevice(c->device));
   const CommBlob *blobs = (const CommBlob *)all_blobs;
+  // every tile maps every other tile's slab: the mailboxes are all-to-all, the fields are
+  // only touched on the four neighbours
+  CommDev hd;
+  memset(&hd, 0, sizeof hd);
+  hd.nranks = c->nranks; hd.rank = c->rank;
+  for (int r = 0; r < c->nranks; r++) {
+    if (blobs[r].rank != r) return tl_fail(c, TL_ERR_ARG, "tl_comm_connect: blobs are not in rank order");
+    if (r == c->rank) { hd.mail[r] = c->mail; continue; }
+    CU(c, cudaIpcOpenMemHandle(&c->rank_slab[r], blobs[r].handle, cudaIpcMemLazyEnablePeerAccess));
+    hd.mail[r] = (MailSlot *)((char *)c->rank_slab[r] + blobs[r].mail_offset);
+  }
+  CU(c, cudaMemcpy(c->d_comm, &hd, sizeof hd, cudaMemcpyHostToDevice));
   for (int s = 0; s < 4; s++) {
     const int nr = c->nbr_rank[s];
     if (nr < 0) continue;
     c->peer_blob[s] = blobs[nr];
-    CU(c, cudaIpcOpenMemHandle(&c->peer_slab[s], blobs[nr].handle, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_slab[s] = c->rank_slab[nr];
   }
 #ifdef TL_WITH_NCCL
   ncclUniqueId id;
@@ -408,6 +434,22 @@ static PeerFace peer_face(tl_ctx *c, int side, int bufidx) {
   f.nx = b.nx; f.ny = b.ny; f.pitch = b.pitch;
   return f;
 }
+
+// halo targets of buffer `bufidx` on the tile-internal sides (fused multi-GPU mode)
+static Push push_for(tl_ctx *c, int bufidx) {
+  Push p;
+  memset(&p, 0, sizeof p);
+  if (c->nranks == 1 || !c->comm_fused) return p;
+  for (int s = 0; s < 4; s++) {
+    if (c->nbr_rank[s] < 0 || !c->peer_slab[s]) continue;
+    const CommBlob &b = c->peer_blob[s];
+    p.s[s].f0 = (double *)((char *)c->peer_slab[s] + b.buf_offset[bufidx]);
+    p.s[s].pitch = b.pitch; p.s[s].nx = b.nx; p.s[s].ny = b.ny;
+  }
+  return p;
+}
+static const CommDev *comm_dev(tl_ctx *c) { return (c->nranks > 1 && c->comm_fused) ? c->d_comm : nullptr; }
+static bool legacy_comm(tl_ctx *c) { return c->nranks > 1 && !c->comm_fused; }
 
 static int buf_index(tl_ctx *c, int f) {
   if (f == TL_P) return c->p_cur ? B_P1 : TL_P;
@@ -712,6 +754,8 @@ static CgAParams cg_a_params(tl_ctx *c) {
   P.r = c->buf[TL_R]; P.p0 = c->buf[TL_P]; P.p1 = c->buf[B_P1]; P.u = c->buf[TL_U];
   P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.w = c->buf[TL_W]; P.partials = c->partials;
   P.single = c->nranks == 1;
+  P.hint_keep = c->hint_keep; P.hint_stream = c->hint_stream;
+  P.cd = comm_dev(c); P.push_p0 = push_for(c, TL_P); P.push_p1 = push_for(c, B_P1);
   return P;
 }
 static CgBParams cg_b_params(tl_ctx *c) {
@@ -719,6 +763,8 @@ static CgBParams cg_b_params(tl_ctx *c) {
   P.g = c->g; P.t = c->pw_tiling; P.st = c->st; P.hist_pw = c->hist_pw;
   P.r = c->buf[TL_R]; P.w = c->buf[TL_W]; P.partials = c->partials;
   P.single = c->nranks == 1;
+  P.hint_keep = c->hint_keep; P.hint_stream = c->hint_stream; P.reverse = c->b_reverse;
+  P.cd = comm_dev(c); P.push_r = push_for(c, TL_R);
   return P;
 }
 
@@ -741,7 +787,7 @@ static int launch_cg_a(tl_ctx *c) {
     case 3: TRY((launch_ring<U, 3, 3>(c, P))); break;
     case 4: TRY((launch_ring<U, 4, 2>(c, P))); break;
     case 6: TRY((launch_ring<U, 6, 1>(c, P))); break;
-    default: k_cg_fused_w<U><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
+    default: return tl_fail(c, TL_ERR_STATE, "internal: ring depth %d", c->ring_eff);
   }
   CHECK_LAUNCH(c);
   return TL_OK;
@@ -766,7 +812,7 @@ static int launch_cheby(tl_ctx *c) {
     case 3: TRY((launch_cheby_ring<FIRST, 3, 3>(c, P))); break;
     case 4: TRY((launch_cheby_ring<FIRST, 4, 2>(c, P))); break;
     case 6: TRY((launch_cheby_ring<FIRST, 6, 1>(c, P))); break;
-    default: k_cheby_fused<FIRST><<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
+    default: return tl_fail(c, TL_ERR_STATE, "internal: ring depth %d", c->ring_eff);
   }
   CHECK_LAUNCH(c);
   return TL_OK;
@@ -789,25 +835,28 @@ static int launch_ppcg_inner(tl_ctx *c) {
     case 3: TRY((launch_ppcg_inner_ring<3, 3>(c, P))); break;
     case 4: TRY((launch_ppcg_inner_ring<4, 2>(c, P))); break;
     case 6: TRY((launch_ppcg_inner_ring<6, 1>(c, P))); break;
-    default: k_ppcg_inner<<<c->fused_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
+    default: return tl_fail(c, TL_ERR_STATE, "internal: ring depth %d", c->ring_eff);
   }
   CHECK_LAUNCH(c);
   return TL_OK;
 }
 
-// One CG iteration on the stream: [halo pulls of r, p when tiled] A, allreduce(pw), B, allreduce(rr).
+// One CG iteration on the stream: kernel A, kernel B.  Tiled (fused mode): the same two kernels --
+// they push their edge cells into the neighbours' halos and sum pw / rr over the tiles in their
+// tails.  Legacy mode (comm_fused = 0, kept for A/B measurements): halo-pull kernels and NCCL.
 static int enqueue_cg_iteration(tl_ctx *c) {
-  if (c->nranks > 1) {
+  const bool legacy = legacy_comm(c);
+  if (legacy) {
     // r is final everywhere after the previous allreduce(rr); p_old after the one before.
     TRY(pull_halo(c, TL_R, 1));
     TRY(pull_halo(c, TL_P, 1));
     TRY(pull_halo(c, B_P1, 1));
   }
   TRY(launch_cg_a<true>(c));
-  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
+  if (legacy) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
   k_cg_fused_r<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
   CHECK_LAUNCH(c);
-  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
+  if (legacy) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
   c->launches += 2;
   return TL_OK;
 }
@@ -851,11 +900,13 @@ static int run_chunks(tl_ctx *c, cudaGraphExec_t *exec, int *exec_iters, int chu
     CU(c, cudaEventRecord(c->ev[k & 1], c->stream));
     if (k >= 1) {
       CU(c, cudaEventSynchronize(c->ev[(k - 1) & 1]));
-      if (stopped(c->h_st[(k - 1) & 1])) break;
+      if (stopped(c->h_st[(k - 1) & 1]) || c->h_st[(k - 1) & 1].comm_error) break;
     }
   }
   CU(c, cudaStreamSynchronize(c->stream));
   *final_state = c->h_st[k & 1];
+  if (final_state->comm_error)
+    return tl_fail(c, TL_ERR_COMM, "tile exchange timed out: a neighbour tile did not reach the same kernel");
   if (!stopped(*final_state)) return tl_fail(c, TL_ERR_STATE, "internal: chunk loop ended before the stop rule fired");
   return TL_OK;
 }
@@ -955,19 +1006,21 @@ static ChebyParams cheby_params(tl_ctx *c) {
   P.u0 = c->buf[TL_U0]; P.ua = c->buf[TL_U]; P.ub = c->buf[B_U1]; P.p = c->buf[TL_P];
   P.w = c->buf[TL_W]; P.r = c->buf[TL_R]; P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
   P.single = c->nranks == 1;
+  P.cd = comm_dev(c); P.push_ua = push_for(c, TL_U); P.push_ub = push_for(c, B_U1);
   return P;
 }
 
-// One Chebyshev iteration.  Tiled: the norm allreduce that ends every iteration (it re-publishes
-// the last norm on iterations that do not compute one) is also the rendezvous that orders the
-// next iteration's halo pull after the neighbours' kernels.
+// One Chebyshev iteration = one kernel.  Tiled (fused mode): the kernel pushes the edge cells of
+// u' into the neighbours' halos; its tail exchange is the norm sum on norm iterations and a plain
+// completion barrier otherwise.  Legacy mode: halo pulls + an NCCL allreduce as the rendezvous.
 static int enqueue_cheby_iteration(tl_ctx *c) {
-  if (c->nranks > 1) {
+  const bool legacy = legacy_comm(c);
+  if (legacy) {
     TRY(pull_halo(c, TL_U, 1));
     TRY(pull_halo(c, B_U1, 1));
   }
   TRY(launch_cheby<false>(c));
-  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_norm_local, &c->st->red_norm, 1));
+  if (legacy) TRY(allreduce2(c, &c->st->red_norm_local, &c->st->red_norm, 1));
   c->launches++;
   return TL_OK;
 }
@@ -1022,10 +1075,12 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
   CHECK_LAUNCH(c);
   // both u buffers must agree outside the cells the fused kernel writes
   LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[TL_U], c->buf[B_U1]);
+  // the first kernel pushes into the neighbours' B_U1 halos: their copy above must be done
+  if (c->nranks > 1) TRY(tile_barrier(c));
   // Cheby.init! field part + bb
   TRY(launch_cheby<true>(c));
   c->launches++;
-  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_norm_local, &c->st->red_norm, 1));
+  if (legacy_comm(c)) TRY(allreduce2(c, &c->st->red_norm_local, &c->st->red_norm, 1));
   double bb = 0.0, error = 0.0;
   TRY(read_scalars(c, &c->st->red_norm, 1, &bb));
   // first main step with the norm, then Cheby.calciter
@@ -1040,7 +1095,7 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
   auto stop = [&](const SolveState &s) { return tl_cheby_should_stop(s); };
   TRY(run_chunks(c, &c->g_cheby, &c->g_cheby_iters, c->graph_iters, 1, enq, stop, &fin));
   c->u_cur = fin.cheby_step & 1;
-  if (c->nranks > 1) {   // haloupdate!(.., [:u]) of the last iteration on the tile-internal sides
+  if (legacy_comm(c)) {   // haloupdate!(.., [:u]) of the last iteration on the tile-internal sides
     TRY(pull_halo(c, c->u_cur ? B_U1 : TL_U, 1));
     TRY(tile_barrier(c));
   }
@@ -1060,6 +1115,7 @@ static PpcgUrParams ppcg_ur_params(tl_ctx *c) {
   P.g = c->g; P.t = c->pw_tiling; P.st = c->st; P.hist_pw = c->hist_pw;
   P.p0 = c->buf[TL_P]; P.p1 = c->buf[B_P1]; P.w = c->buf[TL_W]; P.u = c->buf[TL_U]; P.r = c->buf[TL_R];
   P.sd0 = c->buf[TL_SD];
+  P.partials = c->partials; P.cd = comm_dev(c); P.push_sd0 = push_for(c, TL_SD);
   return P;
 }
 static PpcgInnerParams ppcg_inner_params(tl_ctx *c) {
@@ -1068,30 +1124,34 @@ static PpcgInnerParams ppcg_inner_params(tl_ctx *c) {
   P.sda = c->buf[TL_SD]; P.sdb = c->buf[B_SD1]; P.r = c->buf[TL_R]; P.u = c->buf[TL_U];
   P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
   P.single = c->nranks == 1;
+  P.cd = comm_dev(c); P.push_sda = push_for(c, TL_SD); P.push_sdb = push_for(c, B_SD1); P.push_r = push_for(c, TL_R);
   return P;
 }
 
-// One PPCG outer iteration.  Tiled: depth-1 halos -- r, p before the matvec (ordered by the
-// preceding rr allreduce) and sd before every inner step (ordered by a 1-double rendezvous).
+// One PPCG outer iteration.  Tiled (fused mode): every kernel pushes the operand the next kernel
+// reads through the stencil (p'; sd0; sd'; r after the last inner step) and ends with the tile
+// exchange.  Legacy mode: depth-1 halo pulls -- r, p before the matvec (ordered by the preceding rr
+// allreduce) and sd before every inner step (ordered by a 1-double NCCL rendezvous).
 static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps) {
-  if (c->nranks > 1) {
+  const bool legacy = legacy_comm(c);
+  if (legacy) {
     TRY(pull_halo(c, TL_R, 1));
     TRY(pull_halo(c, TL_P, 1));
     TRY(pull_halo(c, B_P1, 1));
   }
   TRY(launch_cg_a<false>(c));
-  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
+  if (legacy) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
   k_ppcg_ur_sd<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_ur_params(c));
   CHECK_LAUNCH(c);
   for (int pp = 0; pp < inner_steps; pp++) {
-    if (c->nranks > 1) {
+    if (legacy) {
       TRY(tile_barrier(c));
       TRY(pull_halo(c, TL_SD, 1));
       TRY(pull_halo(c, B_SD1, 1));
     }
     TRY(launch_ppcg_inner(c));
   }
-  if (c->nranks > 1) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
+  if (legacy) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
   c->launches += 2 + inner_steps;
   return TL_OK;
 }

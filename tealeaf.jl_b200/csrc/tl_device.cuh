@@ -67,7 +67,27 @@ struct SolveState {
   double red_aux[4];    // field summary / norm2 results
   double theta;
   double eps_cheby;
+  // tile exchange (multi-GPU): number of mailbox exchanges this context has performed since it
+  // was created (never reset: every tile performs the same sequence), and a sticky error flag
+  // raised when a neighbour did not answer within TL_XCHG_TIMEOUT_NS
+  unsigned long long xseq;
+  int comm_error;
+  int pad1;
 };
+
+// ---- multi-GPU: peer-mapped mailboxes and halo push targets --------------------------------
+#define TL_MAX_RANKS 16
+#define TL_XCHG_TIMEOUT_NS 10000000000ull
+// One slot per (parity, sender).  The sender stores v, fences, then releases seq.
+struct MailSlot { double v; unsigned long long seq; };
+struct CommDev {
+  int nranks, rank;
+  MailSlot *mail[TL_MAX_RANKS];   // mail[r] = rank r's mailbox (2 x TL_MAX_RANKS slots), CUDA-IPC mapped
+};
+// Where the edge cells of ONE buffer go: the same buffer of the neighbour tile on each
+// tile-internal side (0 left, 1 right, 2 bottom, 3 top); f0 = interior origin, null on physical sides.
+struct PushSide { double *f0; int pitch, nx, ny; };
+struct Push { PushSide s[4]; };
 
 __host__ __device__ inline bool tl_should_stop(int it, double rr, const StopCfg &c) {
   if (it >= c.max_iters) return true;
@@ -134,8 +154,118 @@ __device__ __forceinline__ bool tl_grid_sum(double (&v)[NV], double *partials, u
   return true;
 }
 
+// ---- tile exchange -------------------------------------------------------------------------
+__device__ __forceinline__ void tl_st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long tl_ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tl_st_relaxed_sys(double *p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double tl_ld_relaxed_sys(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long tl_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// All-tiles sum of one double, executed by the LAST block of a kernel (all of its threads call
+// this; `v` is valid in thread 0).  Thread q stores this tile's value into tile q's mailbox over
+// NVLink (fire-and-forget peer stores), then waits for tile q's value to land in the local
+// mailbox; thread 0 adds the values in rank order, so every tile gets the same bits.  Because
+// every block of this kernel fenced its peer stores (halo pushes) at system scope before taking
+// its ticket, a tile that has received our slot also sees our pushed halo cells: the exchange is
+// the halo-exchange completion barrier as well.  Slots are double-buffered by the parity of the
+// exchange number; exchange n+2 can only start after every tile finished reading exchange n.
+__device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState *st, double v, double *sm) {
+  __shared__ unsigned long long s_seq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sm[0] = v;
+    s_seq = st->xseq + 1;
+    st->xseq = s_seq;
+  }
+  __syncthreads();
+  const int n = cd->nranks;
+  const unsigned long long seq = s_seq;
+  const int par = (int)(seq & 1ull);
+  if ((int)threadIdx.x < n) {
+    MailSlot *dst = cd->mail[threadIdx.x] + par * TL_MAX_RANKS + cd->rank;
+    tl_st_relaxed_sys(&dst->v, sm[0]);
+    __threadfence_system();
+    tl_st_release_sys(&dst->seq, seq);
+    const MailSlot *src = cd->mail[cd->rank] + par * TL_MAX_RANKS + threadIdx.x;
+    const unsigned long long t0 = tl_globaltimer();
+    while (tl_ld_acquire_sys(&src->seq) != seq) {
+      if (tl_globaltimer() - t0 > TL_XCHG_TIMEOUT_NS) { st->comm_error = 1; break; }
+    }
+    sm[1 + threadIdx.x] = tl_ld_relaxed_sys(&src->v);
+  }
+  __syncthreads();
+  double total = 0.0;
+  if (threadIdx.x == 0)
+    for (int r = 0; r < n; r++) total += sm[1 + r];
+  return total;
+}
+
+// Common end of a hot-loop kernel: grid-wide sum of acc[0] (do_sum) or just the last-block
+// ticket, then -- when tiles exchange (cd != null) -- the all-tiles sum / barrier.  Returns true
+// in thread 0 of the last block, with acc[0] = the (global) total.
+__device__ __forceinline__ bool tl_kernel_tail(double (&acc)[1], bool do_sum, bool pushed, SolveState *st,
+                                               double *partials, const CommDev *cd, double *sm) {
+  if (pushed) __threadfence_system();   // this lane's halo pushes are performed before the ticket
+  bool last;
+  if (do_sum) {
+    last = tl_grid_sum<1>(acc, partials, &st->counter, sm);
+  } else {
+    __shared__ bool s_last_nosum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last_nosum = (atomicAdd(&st->counter, 1u) == gridDim.x - 1);
+      if (s_last_nosum) { __threadfence(); st->counter = 0u; }
+    }
+    __syncthreads();
+    last = s_last_nosum;
+    acc[0] = 0.0;
+  }
+  if (!last) return false;
+  if (cd) acc[0] = tl_tile_exchange(cd, st, acc[0], sm);
+  return threadIdx.x == 0;
+}
+
 __device__ __forceinline__ double2 tl_ld2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 __device__ __forceinline__ double2 tl_ld2_rw(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void tl_st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+
+// L2 eviction-priority policies (createpolicy) and accesses that carry one.  Used by the CG
+// kernels to keep r and w (the only operands re-touched by the NEXT kernel) resident in the
+// 126 MB L2 while everything else streams through it.
+#define TL_HINT_NORMAL 0
+#define TL_HINT_FIRST 1
+#define TL_HINT_LAST 2
+__device__ __forceinline__ unsigned long long tl_policy(int kind) {
+  unsigned long long p;
+  if (kind == TL_HINT_FIRST) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == TL_HINT_LAST) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double2 tl_ld2_hint(const double *p, unsigned long long pol) {
+  double2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tl_st2_hint(double *p, double2 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
 
 #endif  // __CUDACC__

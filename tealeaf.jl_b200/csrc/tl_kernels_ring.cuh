@@ -1,8 +1,11 @@
-// tl_kernels_ring.cuh -- shared-memory ring variants of the stencil kernels.
+// tl_kernels_ring.cuh -- the hot path, part 2: the stencil kernels (CG kernel A, the Chebyshev
+// iteration, the PPCG inner step).
 //
-// Same warp-strip marching as tl_kernels_fused.cuh, but the loads for the next S-1 rows are in
-// flight as asynchronous global->shared copies (cp.async / LDGSTS, 16 B per lane) instead of
-// sitting in registers: every warp owns a private ring of S row-slots in shared memory, each lane
+// Warp-strip marching (tl_kernels_fused.cuh): the stencil operand of rows j-1, j, j+1 is carried
+// in registers, so every field is read from HBM once; x-neighbours come from warp shuffles, and
+// only lanes 0/31 fetch one extra scalar per row from the neighbouring strip.  The loads for the
+// next S-1 rows are in flight as asynchronous global->shared copies (cp.async / LDGSTS, 16 B per
+// lane): every warp owns a private ring of S row-slots in shared memory, each lane
 // reads back only the bytes it copied itself, so no barrier of any kind is needed -- completion
 // is tracked per thread with cp.async commit/wait groups.  The memory system then sees
 // (S-1) x 2.5 KB per warp in flight (vs 2.5 KB with register double-buffering), which is what an
@@ -16,6 +19,9 @@
 __device__ __forceinline__ unsigned tl_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tl_cp16(unsigned dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tl_cp16_hint(unsigned dst, const void *src, unsigned long long pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void tl_cp8(unsigned dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
@@ -34,7 +40,7 @@ __device__ __forceinline__ double tl_lds1(unsigned a) {
   return v;
 }
 
-// CG kernel A, ring variant (see k_cg_fused_w for the algorithm and the citations).
+// CG kernel A (algorithm and citations: CgAParams in tl_kernels_fused.cuh).
 template <bool UPDATE_U, int S, int MINB>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(const CgAParams P) {
   extern __shared__ __align__(128) unsigned char ring_raw[];
@@ -42,7 +48,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
   SolveState *st = P.st;
   const int it = st->iter;
   const double rr_cur = st->red_rr;
-  if (tl_should_stop(it, rr_cur, st->cfg)) return;
+  if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
   const bool first = (it == st->cfg.first_it);
   double beta = 0.0, alpha_prev = 0.0;
   if (!first) {
@@ -63,6 +69,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
   const bool physL = g.phys & TL_PHYS_LEFT, physR = g.phys & TL_PHYS_RIGHT;
   const bool physB = g.phys & TL_PHYS_BOTTOM, physT = g.phys & TL_PHYS_TOP;
 
+  const unsigned long long pol_keep = tl_policy(P.hint_keep), pol_stream = tl_policy(P.hint_stream);
+  const bool tiled = P.cd != nullptr;
+  const Push &push = (it & 1) ? P.push_p0 : P.push_p1;   // halo targets of pout
+  bool pushed = false;
   double acc[1] = {0.0};
   MarchCtx m;
   if (tl_march_setup(g, P.t, m)) {
@@ -78,12 +88,12 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
       const int jn = (j + 1 >= g.ny && physT) ? g.ny - 1 : j + 1;
       const long on = (long)jn * pitch + m.i0, oc = (long)j * pitch + m.i0;
       if (m.ld_ok) {
-        tl_cp16(base + 0 * 512 + lane_off, r + on);
-        tl_cp16(base + 1 * 512 + lane_off, pin + on);
-        tl_cp16(base + 2 * 512 + lane_off, ky + oc + pitch);
-        tl_cp16(base + 3 * 512 + lane_off, kx + oc);
+        tl_cp16_hint(base + 0 * 512 + lane_off, r + on, pol_keep);
+        tl_cp16_hint(base + 1 * 512 + lane_off, pin + on, pol_stream);
+        tl_cp16_hint(base + 2 * 512 + lane_off, ky + oc + pitch, pol_stream);
+        tl_cp16_hint(base + 3 * 512 + lane_off, kx + oc, pol_stream);
       }
-      if (UPDATE_U && m.acta) tl_cp16(base + 4 * 512 + lane_off, u + oc);
+      if (UPDATE_U && m.acta) tl_cp16_hint(base + 4 * 512 + lane_off, u + oc, pol_stream);
       if (m.has_edge) {
         const long oe = (long)jn * pitch + m.ecol;
         tl_cp8(base + edge_off + 0, r + oe);
@@ -149,9 +159,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
       double2 un = z2;
       if (UPDATE_U) un = make_double2(c_u.x + alpha_prev * pc.x, c_u.y + alpha_prev * pc.y);
       if (m.actb) {
-        tl_st2(w + oc, make_double2(wa, wb));
-        tl_st2(pout + oc, Xc);
-        if (UPDATE_U) tl_st2(u + oc, un);
+        tl_st2_hint(w + oc, make_double2(wa, wb), pol_keep);
+        tl_st2_hint(pout + oc, Xc, pol_stream);
+        if (UPDATE_U) tl_st2_hint(u + oc, un, pol_stream);
         acc[0] += wa * Xc.x;
         acc[0] += wb * Xc.y;
       } else if (m.acta) {
@@ -159,26 +169,18 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
         if (UPDATE_U) u[oc] = un.x;
         acc[0] += wa * Xc.x;
       }
-      if (m.acta) {
-        if (physL && m.i0 == 0) { pout[oc - 1] = Xc.x; if (UPDATE_U) u[oc - 1] = un.x; }
-        if (physR && m.i0 == g.nx - 1) { pout[oc + 1] = Xc.x; if (UPDATE_U) u[oc + 1] = un.x; }
-        if (physR && m.i0 + 1 == g.nx - 1) { pout[oc + 2] = Xc.y; if (UPDATE_U) u[oc + 2] = un.y; }
-        if (physB && j == 0) {
-          pout[oc - pitch] = Xc.x; if (UPDATE_U) u[oc - pitch] = un.x;
-          if (m.actb) { pout[oc - pitch + 1] = Xc.y; if (UPDATE_U) u[oc - pitch + 1] = un.y; }
-        }
-        if (physT && j == g.ny - 1) {
-          pout[oc + pitch] = Xc.x; if (UPDATE_U) u[oc + pitch] = un.x;
-          if (m.actb) { pout[oc + pitch + 1] = Xc.y; if (UPDATE_U) u[oc + pitch + 1] = un.y; }
-        }
-      }
+      // haloupdate!(.., [:u,:p]) CG.jl:22: reflective sides as a write-through, tile-internal
+      // sides as a push of p into the neighbour's halo (u's internal halos are filled after the loop)
+      tl_reflect_edges(pout, g, m, j, oc, Xc);
+      if (UPDATE_U) tl_reflect_edges(u, g, m, j, oc, un);
+      if (tiled) pushed |= tl_push_edges(push, g, m, j, Xc);
       Xm = Xc; Xc = Xn; XcE = XnE; pc = c_p; kyc = c_ky;
     }
     tl_cp_wait<0>();
   }
-  if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) {
+  if (tl_kernel_tail(acc, true, pushed, st, P.partials, P.cd, sm)) {
     st->red_pw_local = acc[0];
-    if (P.single) st->red_pw = acc[0];
+    if (P.single || tiled) st->red_pw = acc[0];
   }
 }
 
@@ -258,7 +260,7 @@ __device__ __forceinline__ void tl_stencil2(const Geo &g, const MarchCtx &m, boo
   wb = ((((1.0 + kxr) + kxv.y) + kyn.y) + kyc.y) * Xc.y - (kxr * Rb + kxv.y * Lb) - (kyn.y * Xn.y + kyc.y * Xm.y);
 }
 
-// Chebyshev iteration, ring variant (see k_cheby_fused).
+// Chebyshev iteration (algorithm and citations: ChebyParams in tl_kernels_fused.cuh).
 template <bool FIRST, int S, int MINB>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(const ChebyParams P) {
   extern __shared__ __align__(128) unsigned char ring_raw[];
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
     calc_norm = true;
     store_wr = true;
   } else {
-    if (tl_cheby_should_stop(*st)) return;
+    if (st->comm_error || tl_cheby_should_stop(*st)) return;
     const int chebyiters = step;
     const int tt = st->cheby_tt0 + chebyiters - 1;
     alpha = P.alphas[chebyiters];
@@ -282,6 +284,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
   }
   const double *__restrict__ uin = (step & 1) ? P.ub : P.ua;
   double *__restrict__ uout = (step & 1) ? P.ua : P.ub;
+  const bool tiled = P.cd != nullptr;
+  const Push &push = (step & 1) ? P.push_ua : P.push_ub;   // halo targets of uout
+  bool pushed = false;
   const double *__restrict__ u0 = P.u0;
   const double *__restrict__ kx = P.kx;
   const double *__restrict__ ky = P.ky;
@@ -337,45 +342,39 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
         if (store_wr) { P.w[oc] = wa; P.r[oc] = ra; }
         acc[0] += FIRST ? cur.a.x * cur.a.x : ra * ra;
       }
-      if (m.acta) {
-        if (physL && m.i0 == 0) uout[oc - 1] = un.x;
-        if (physR && m.i0 == g.nx - 1) uout[oc + 1] = un.x;
-        if (physR && m.i0 + 1 == g.nx - 1) uout[oc + 2] = un.y;
-        if (physB && j == 0) { uout[oc - pitch] = un.x; if (m.actb) uout[oc - pitch + 1] = un.y; }
-        if (physT && j == g.ny - 1) { uout[oc + pitch] = un.x; if (m.actb) uout[oc + pitch + 1] = un.y; }
-      }
+      // haloupdate!(.., [:u]) Cheby.jl:55/:78
+      tl_reflect_edges(uout, g, m, j, oc, un);
+      if (tiled) pushed |= tl_push_edges(push, g, m, j, un);
       Xm = Xc; Xc = Xn; XcE = cur.xe; kyc = cur.ky;
     }
     tl_cp_wait<0>();
   }
-  if (calc_norm) {
-    if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) {
+  // no reduction on most iterations: only the ticket (and, tiled, the completion barrier)
+  if (tl_kernel_tail(acc, calc_norm, pushed, st, P.partials, P.cd, sm)) {
+    if (calc_norm) {
       st->red_norm_local = acc[0];
-      if (P.single) st->red_norm = acc[0];
-      st->cheby_step = step + 1;
+      if (P.single || tiled) st->red_norm = acc[0];
     }
-  } else {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(&st->counter, 1u) == gridDim.x - 1) { st->counter = 0u; st->cheby_step = step + 1; }
-    }
+    st->cheby_step = step + 1;
   }
 }
 
-// PPCG inner step, ring variant (see k_ppcg_inner).
+// PPCG inner step (algorithm and citations: PpcgInnerParams in tl_kernels_fused.cuh).
 template <int S, int MINB>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(const PpcgInnerParams P) {
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
   const int it = st->iter;
-  if (tl_should_stop(it, st->red_rr, st->cfg)) return;
+  if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
   const int pp = st->inner_pp;
   const bool last = (pp + 1 == st->inner_steps);
   const double alpha = P.alphas[pp], beta = P.betas[pp];
   const double *__restrict__ sin = (pp & 1) ? P.sdb : P.sda;
   double *__restrict__ sout = (pp & 1) ? P.sda : P.sdb;
+  const bool tiled = P.cd != nullptr;
+  const Push &push = (pp & 1) ? P.push_sda : P.push_sdb;   // halo targets of sout
+  bool pushed = false;
   const double *__restrict__ kx = P.kx;
   const double *__restrict__ ky = P.ky;
   double *__restrict__ r = P.r;
@@ -426,30 +425,22 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(cons
         r[oc] = rn.x; u[oc] = un.x; sout[oc] = sn.x;
         acc[0] += rn.x * rn.x;
       }
-      if (m.acta) {
-        const double ha = last ? Xc.x : sn.x, hb = last ? Xc.y : sn.y;
-        if (physL && m.i0 == 0) sout[oc - 1] = ha;
-        if (physR && m.i0 == g.nx - 1) sout[oc + 1] = ha;
-        if (physR && m.i0 + 1 == g.nx - 1) sout[oc + 2] = hb;
-        if (physB && j == 0) { sout[oc - pitch] = ha; if (m.actb) sout[oc - pitch + 1] = hb; }
-        if (physT && j == g.ny - 1) { sout[oc + pitch] = ha; if (m.actb) sout[oc + pitch + 1] = hb; }
-      }
+      // halo(sd) of PPCG.jl:76 happens BEFORE each inner step, so after the last step memory
+      // holds the reflection of the step's *input*; earlier steps leave the output's.
+      tl_reflect_edges(sout, g, m, j, oc, last ? Xc : sn);
+      // tiled: the next inner step reads the neighbours' sd'; after the last step the next
+      // outer iteration's matvec reads their r (p = r + beta p is recomputed at the neighbours)
+      if (tiled) pushed |= last ? tl_push_edges(P.push_r, g, m, j, rn) : tl_push_edges(push, g, m, j, sn);
       Xm = Xc; Xc = Xn; XcE = cur.xe; kyc = cur.ky;
     }
     tl_cp_wait<0>();
   }
-  if (last) {
-    if (tl_grid_sum<1>(acc, P.partials, &st->counter, sm) && threadIdx.x == 0) {
-      st->red_rr_local = acc[0];
-      if (P.single) st->red_rr = acc[0];
+  if (tl_kernel_tail(acc, last, pushed, st, P.partials, P.cd, sm)) {
+    if (last) {
+      st->red_rr_local = acc[0];      // PPCG.jl:88
+      if (P.single || tiled) st->red_rr = acc[0];
       st->iter = it + 1;
-      st->inner_pp = pp + 1;
     }
-  } else {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(&st->counter, 1u) == gridDim.x - 1) { st->counter = 0u; st->inner_pp = pp + 1; }
-    }
+    st->inner_pp = pp + 1;
   }
 }

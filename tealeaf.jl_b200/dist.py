@@ -5,8 +5,10 @@ in the reference: none"); its `haloupdate!` vocabulary ("exchange") comes from t
 upstream.  Here the global `xcells x ycells` interior is cut into a `px x py` grid of tiles
 (y, the strided dimension, is split first so that most exchanged faces are contiguous rows).
 Plumbing is `torch.distributed` (NCCL on GPUs, gloo in the CPU tests); the data path is
-inside libtealeaf_b200: neighbours' edge cells are read directly from their memory over
-NVLink (CUDA-IPC mapped pointers), dot products are NCCL allreduces captured in the CUDA graphs.
+inside libtealeaf_b200: every tile maps the other tiles' memory (CUDA-IPC), the solver kernels
+store their edge cells straight into the neighbours' halo cells over NVLink and sum the dot
+products through peer-mapped mailboxes in their tails (option comm_fused=0 selects the older
+halo-pull kernels + NCCL allreduces).
 """
 from __future__ import annotations
 
@@ -18,6 +20,13 @@ from .settings import Settings
 
 def grid_for(world: int):
     """px x py for `world` ranks: 1x1, 1x2, 2x2, 2x4, else the squarest split."""
+    import os
+    env = os.environ.get("TEALEAF_GRID")          # e.g. "1x4": override (tests, experiments)
+    if env:
+        px, py = (int(v) for v in env.lower().split("x"))
+        if px * py != world:
+            raise ValueError(f"TEALEAF_GRID={env} does not match {world} ranks")
+        return px, py
     table = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
     if world in table:
         return table[world]
@@ -53,7 +62,7 @@ def connect(chunk, dist):
     chunk.comm_connect(blobs, ident[0])
 
 
-def create_tile(settings: Settings, dist, device: int, backend=None):
+def create_tile(settings: Settings, dist, device: int, backend=None, options=None):
     """`initialiseapp!` for this rank's tile.  Returns (chunk, geom, (px, py))."""
     from .app import upload_initial_state
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -64,6 +73,8 @@ def create_tile(settings: Settings, dist, device: int, backend=None):
         backend = DeviceChunk
     chunk = backend(tnx, tny, settings.halodepth, settings.maxiters, device=device, rank=rank, px=px, py=py)
     connect(chunk, dist)
+    for k, v in (options or {}).items():
+        chunk.set_option(k, v)
     geom = HostGeometry(settings, tile=(x0, y0, tnx, tny))
     upload_initial_state(chunk, settings, geom)
     return chunk, geom, (px, py)

@@ -14,10 +14,11 @@ from conftest import classic_settings
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _torchrun(script, nproc, *args, timeout=900):
+def _torchrun(script, nproc, *args, timeout=900, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "tests", script), *args]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT,
+                          env={**os.environ, **(env or {})})
 
 
 def test_decomposition_helpers():
@@ -45,11 +46,21 @@ def test_gloo_world2_host_plumbing():
 
 
 @pytest.mark.gpu
-def test_tiled_solvers_match_oracle():
+@pytest.mark.parametrize("grid", ["default", "x-split", "y-split"])
+def test_tiled_solvers_match_oracle(grid):
+    """Every solver tiled over all GPUs of the box vs the single-chunk oracle: the default
+    decomposition (1x2, 2x2, 2x4) and the two 1-D splits (tiles with neighbours on both sides)."""
     import torch
-    n = torch.cuda.device_count()
+    n = min(torch.cuda.device_count(), 8)
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
-    r = _torchrun("mgpu_check.py", min(n, 8))
+    env = {}
+    if grid == "x-split":
+        env["TEALEAF_GRID"] = f"{n}x1"
+    elif grid == "y-split":
+        if n == 2:
+            pytest.skip("1x2 is the default decomposition on 2 GPUs")
+        env["TEALEAF_GRID"] = f"1x{n}"
+    r = _torchrun("mgpu_check.py", n, env=env)
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
