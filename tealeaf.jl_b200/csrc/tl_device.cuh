@@ -78,8 +78,10 @@ struct SolveState {
 // ---- multi-GPU: peer-mapped mailboxes and halo push targets --------------------------------
 #define TL_MAX_RANKS 16
 #define TL_XCHG_TIMEOUT_NS 10000000000ull
-// One slot per (parity, sender).  The sender stores v, fences, then releases seq.
-struct MailSlot { double v; unsigned long long seq; };
+// One slot per (parity, sender), "LL" packets: each 8-byte word carries 32 bits of the double and
+// the low 32 bits of the exchange number, so one (atomic) 8-byte store publishes data and flag
+// together and no fence sits between them.
+struct MailSlot { unsigned long long lo, hi; };
 struct CommDev {
   int nranks, rank;
   MailSlot *mail[TL_MAX_RANKS];   // mail[r] = rank r's mailbox (2 x TL_MAX_RANKS slots), CUDA-IPC mapped
@@ -129,7 +131,8 @@ __device__ __forceinline__ double tl_block_sum(double v, double *sm) {
 // last block, with the total valid in thread 0 of that block.  No FP64 atomics, so results
 // are run-to-run reproducible.  `NV` values are reduced at once.
 template <int NV>
-__device__ __forceinline__ bool tl_grid_sum(double (&v)[NV], double *partials, unsigned *counter, double *sm) {
+__device__ __forceinline__ bool tl_grid_sum(double (&v)[NV], double *partials, unsigned *counter, double *sm,
+                                            bool sys_fence = false) {
   __shared__ bool s_last;
 #pragma unroll
   for (int q = 0; q < NV; q++) {
@@ -144,6 +147,9 @@ __device__ __forceinline__ bool tl_grid_sum(double (&v)[NV], double *partials, u
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
+  // tiles exchange after this sum: one thread makes everything this GPU wrote (the halo pushes
+  // of all blocks, ordered before their tickets) visible system-wide while the others add up
+  if (sys_fence && threadIdx.x == blockDim.x - 1) __threadfence_system();
 #pragma unroll
   for (int q = 0; q < NV; q++) {
     double t = 0.0;
@@ -155,20 +161,12 @@ __device__ __forceinline__ bool tl_grid_sum(double (&v)[NV], double *partials, u
 }
 
 // ---- tile exchange -------------------------------------------------------------------------
-__device__ __forceinline__ void tl_st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void tl_st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long tl_ld_acquire_sys(const unsigned long long *p) {
+__device__ __forceinline__ unsigned long long tl_ld_relaxed_sys(const unsigned long long *p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void tl_st_relaxed_sys(double *p, double v) {
-  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ double tl_ld_relaxed_sys(const double *p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long tl_globaltimer() {
@@ -180,11 +178,16 @@ __device__ __forceinline__ unsigned long long tl_globaltimer() {
 // All-tiles sum of one double, executed by the LAST block of a kernel (all of its threads call
 // this; `v` is valid in thread 0).  Thread q stores this tile's value into tile q's mailbox over
 // NVLink (fire-and-forget peer stores), then waits for tile q's value to land in the local
-// mailbox; thread 0 adds the values in rank order, so every tile gets the same bits.  Because
-// every block of this kernel fenced its peer stores (halo pushes) at system scope before taking
-// its ticket, a tile that has received our slot also sees our pushed halo cells: the exchange is
-// the halo-exchange completion barrier as well.  Slots are double-buffered by the parity of the
-// exchange number; exchange n+2 can only start after every tile finished reading exchange n.
+// mailbox; thread 0 adds the values in rank order, so every tile gets the same bits.
+//
+// Ordering of the halo pushes: every block of this kernel ordered its peer stores before its
+// ticket (bar.sync + fence.gpu + atomic), the last block observed all tickets and one of its
+// threads executed fence.sys before the barrier that precedes the mailbox stores below -- the
+// pattern cooperative groups' multi-grid sync uses.  A tile that has received our slot therefore
+// also sees our pushed halo cells: the exchange is the halo-exchange completion barrier as well
+// (and, being all-to-all, a full execution barrier: WAR hazards on the ping-pong buffers).
+// Slots are double-buffered by the parity of the exchange number; exchange n+2 can only start
+// after every tile finished reading exchange n.
 __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState *st, double v, double *sm) {
   __shared__ unsigned long long s_seq;
   __syncthreads();
@@ -195,21 +198,31 @@ __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState
   }
   __syncthreads();
   const int n = cd->nranks;
-  const unsigned long long seq = s_seq;
-  const int par = (int)(seq & 1ull);
+  const unsigned seq = (unsigned)s_seq;
+  const int par = (int)(seq & 1u);
   if ((int)threadIdx.x < n) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(sm[0]);
     MailSlot *dst = cd->mail[threadIdx.x] + par * TL_MAX_RANKS + cd->rank;
-    tl_st_relaxed_sys(&dst->v, sm[0]);
-    __threadfence_system();
-    tl_st_release_sys(&dst->seq, seq);
+    tl_st_relaxed_sys(&dst->lo, ((unsigned long long)seq << 32) | (bits & 0xffffffffull));
+    tl_st_relaxed_sys(&dst->hi, ((unsigned long long)seq << 32) | (bits >> 32));
     const MailSlot *src = cd->mail[cd->rank] + par * TL_MAX_RANKS + threadIdx.x;
-    const unsigned long long t0 = tl_globaltimer();
-    while (tl_ld_acquire_sys(&src->seq) != seq) {
-      if (tl_globaltimer() - t0 > TL_XCHG_TIMEOUT_NS) { st->comm_error = 1; break; }
+    unsigned long long lo, hi;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+      lo = tl_ld_relaxed_sys(&src->lo);
+      hi = tl_ld_relaxed_sys(&src->hi);
+      if ((unsigned)(lo >> 32) == seq && (unsigned)(hi >> 32) == seq) break;
+      if ((++spins & 1023u) == 0u) {   // a neighbour that never arrives must not hang the GPU
+        const unsigned long long t = tl_globaltimer();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > TL_XCHG_TIMEOUT_NS) { st->comm_error = 1; break; }
+      }
     }
-    sm[1 + threadIdx.x] = tl_ld_relaxed_sys(&src->v);
+    sm[1 + threadIdx.x] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
   }
   __syncthreads();
+  __threadfence_system();   // acquire side: later reads (the next kernel's halo loads) see the neighbours' pushes
   double total = 0.0;
   if (threadIdx.x == 0)
     for (int r = 0; r < n; r++) total += sm[1 + r];
@@ -219,19 +232,21 @@ __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState
 // Common end of a hot-loop kernel: grid-wide sum of acc[0] (do_sum) or just the last-block
 // ticket, then -- when tiles exchange (cd != null) -- the all-tiles sum / barrier.  Returns true
 // in thread 0 of the last block, with acc[0] = the (global) total.
-__device__ __forceinline__ bool tl_kernel_tail(double (&acc)[1], bool do_sum, bool pushed, SolveState *st,
-                                               double *partials, const CommDev *cd, double *sm) {
-  if (pushed) __threadfence_system();   // this lane's halo pushes are performed before the ticket
+__device__ __forceinline__ bool tl_kernel_tail(double (&acc)[1], bool do_sum, SolveState *st, double *partials,
+                                               const CommDev *cd, double *sm) {
   bool last;
   if (do_sum) {
-    last = tl_grid_sum<1>(acc, partials, &st->counter, sm);
+    last = tl_grid_sum<1>(acc, partials, &st->counter, sm, cd != nullptr);
   } else {
     __shared__ bool s_last_nosum;
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
       s_last_nosum = (atomicAdd(&st->counter, 1u) == gridDim.x - 1);
-      if (s_last_nosum) { __threadfence(); st->counter = 0u; }
+      if (s_last_nosum) {
+        if (cd) __threadfence_system(); else __threadfence();
+        st->counter = 0u;
+      }
     }
     __syncthreads();
     last = s_last_nosum;

@@ -46,29 +46,23 @@ __device__ __forceinline__ bool tl_march_setup(const Geo &g, const Tiling &t, Ma
 }
 
 // Stores this lane's cells (i0, i0+1) of row j into the neighbours' depth-1 halo cells when they
-// lie on a tile-internal edge.  Returns true if a peer store was issued.
-__device__ __forceinline__ bool tl_push_edges(const Push &ps, const Geo &g, const MarchCtx &m, int j, double2 v) {
-  if (!m.acta) return false;
-  bool pushed = false;
-  if (ps.s[0].f0 && m.i0 == 0) {                       // my column 0 -> left tile's column nx_left
+// lie on a tile-internal edge (plain peer stores; tl_tile_exchange explains their ordering).
+__device__ __forceinline__ void tl_push_edges(const Push &ps, const Geo &g, const MarchCtx &m, int j, double2 v) {
+  if (!m.acta) return;
+  if (ps.s[0].f0 && m.i0 == 0)                         // my column 0 -> left tile's column nx_left
     ps.s[0].f0[(long)j * ps.s[0].pitch + ps.s[0].nx] = v.x;
-    pushed = true;
-  }
   if (ps.s[1].f0) {                                    // my column nx-1 -> right tile's column -1
-    if (m.i0 == g.nx - 1) { ps.s[1].f0[(long)j * ps.s[1].pitch - 1] = v.x; pushed = true; }
-    else if (m.i0 + 1 == g.nx - 1) { ps.s[1].f0[(long)j * ps.s[1].pitch - 1] = v.y; pushed = true; }
+    if (m.i0 == g.nx - 1) ps.s[1].f0[(long)j * ps.s[1].pitch - 1] = v.x;
+    else if (m.i0 + 1 == g.nx - 1) ps.s[1].f0[(long)j * ps.s[1].pitch - 1] = v.y;
   }
   if (ps.s[2].f0 && j == 0) {                          // my row 0 -> bottom tile's row ny_bottom
     double *d = ps.s[2].f0 + (long)ps.s[2].ny * ps.s[2].pitch + m.i0;
     if (m.actb) tl_st2(d, v); else d[0] = v.x;
-    pushed = true;
   }
   if (ps.s[3].f0 && j == g.ny - 1) {                   // my row ny-1 -> top tile's row -1
     double *d = ps.s[3].f0 - ps.s[3].pitch + m.i0;
     if (m.actb) tl_st2(d, v); else d[0] = v.x;
-    pushed = true;
   }
-  return pushed;
 }
 
 // Depth-1 reflective halo of one field as a write-through (haloupdate!, kernels.jl:191-210)
@@ -135,7 +129,6 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBPar
   const double *__restrict__ w = P.w;
   const unsigned long long pol_r = tl_policy(P.hint_keep), pol_w = tl_policy(P.hint_stream);
   const bool tiled = P.cd != nullptr;
-  bool pushed = false;
   double acc[1] = {0.0};
   MarchCtx m;
   if (tl_march_setup(g, P.t, m, P.reverse)) {
@@ -157,7 +150,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBPar
           tl_st2_hint(r + o, rv[q], pol_r);
           acc[0] += rv[q].x * rv[q].x;
           acc[0] += rv[q].y * rv[q].y;
-          if (tiled) pushed |= tl_push_edges(P.push_r, g, m, j + q, rv[q]);
+          if (tiled) tl_push_edges(P.push_r, g, m, j + q, rv[q]);
         }
       }
     }
@@ -166,10 +159,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBPar
       double2 v = make_double2(0.0, 0.0);
       if (m.acta) { v.x = r[o] - alpha * w[o]; r[o] = v.x; acc[0] += v.x * v.x; }
       if (m.actb) { v.y = r[o + 1] - alpha * w[o + 1]; r[o + 1] = v.y; acc[0] += v.y * v.y; }
-      if (tiled) pushed |= tl_push_edges(P.push_r, g, m, j, v);
+      if (tiled) tl_push_edges(P.push_r, g, m, j, v);
     }
   }
-  if (tl_kernel_tail(acc, true, pushed, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
     st->red_rr_local = acc[0];
     if (P.single || tiled) st->red_rr = acc[0];
     st->iter = it + 1;
@@ -282,7 +275,6 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_ppcg_ur_sd(const PpcgUr
   const double *__restrict__ p = (it & 1) ? P.p0 : P.p1;
   const Geo g = P.g;
   const bool tiled = P.cd != nullptr;
-  bool pushed = false;
   MarchCtx m;
   if (tl_march_setup(g, P.t, m)) {
     for (int j = m.j0; j < m.j1; j++) {
@@ -299,12 +291,12 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_ppcg_ur_sd(const PpcgUr
         P.sd0[o] = s;
         if (c == 0) sv.x = s; else sv.y = s;
       }
-      if (tiled) pushed |= tl_push_edges(P.push_sd0, g, m, j, sv);
+      if (tiled) tl_push_edges(P.push_sd0, g, m, j, sv);
     }
   }
   if (tiled) {   // the first inner step reads the neighbours' sd: completion barrier
     double acc[1] = {0.0};
-    tl_kernel_tail(acc, false, pushed, st, P.partials, P.cd, sm);
+    tl_kernel_tail(acc, false, st, P.partials, P.cd, sm);
   }
 }
 

@@ -72,7 +72,6 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
   const unsigned long long pol_keep = tl_policy(P.hint_keep), pol_stream = tl_policy(P.hint_stream);
   const bool tiled = P.cd != nullptr;
   const Push &push = (it & 1) ? P.push_p0 : P.push_p1;   // halo targets of pout
-  bool pushed = false;
   double acc[1] = {0.0};
   MarchCtx m;
   if (tl_march_setup(g, P.t, m)) {
@@ -173,12 +172,12 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
       // sides as a push of p into the neighbour's halo (u's internal halos are filled after the loop)
       tl_reflect_edges(pout, g, m, j, oc, Xc);
       if (UPDATE_U) tl_reflect_edges(u, g, m, j, oc, un);
-      if (tiled) pushed |= tl_push_edges(push, g, m, j, Xc);
+      if (tiled) tl_push_edges(push, g, m, j, Xc);
       Xm = Xc; Xc = Xn; XcE = XnE; pc = c_p; kyc = c_ky;
     }
     tl_cp_wait<0>();
   }
-  if (tl_kernel_tail(acc, true, pushed, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
     st->red_pw_local = acc[0];
     if (P.single || tiled) st->red_pw = acc[0];
   }
@@ -286,7 +285,6 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
   double *__restrict__ uout = (step & 1) ? P.ua : P.ub;
   const bool tiled = P.cd != nullptr;
   const Push &push = (step & 1) ? P.push_ua : P.push_ub;   // halo targets of uout
-  bool pushed = false;
   const double *__restrict__ u0 = P.u0;
   const double *__restrict__ kx = P.kx;
   const double *__restrict__ ky = P.ky;
@@ -344,13 +342,13 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
       }
       // haloupdate!(.., [:u]) Cheby.jl:55/:78
       tl_reflect_edges(uout, g, m, j, oc, un);
-      if (tiled) pushed |= tl_push_edges(push, g, m, j, un);
+      if (tiled) tl_push_edges(push, g, m, j, un);
       Xm = Xc; Xc = Xn; XcE = cur.xe; kyc = cur.ky;
     }
     tl_cp_wait<0>();
   }
   // no reduction on most iterations: only the ticket (and, tiled, the completion barrier)
-  if (tl_kernel_tail(acc, calc_norm, pushed, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, calc_norm, st, P.partials, P.cd, sm)) {
     if (calc_norm) {
       st->red_norm_local = acc[0];
       if (P.single || tiled) st->red_norm = acc[0];
@@ -374,7 +372,6 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(cons
   double *__restrict__ sout = (pp & 1) ? P.sda : P.sdb;
   const bool tiled = P.cd != nullptr;
   const Push &push = (pp & 1) ? P.push_sda : P.push_sdb;   // halo targets of sout
-  bool pushed = false;
   const double *__restrict__ kx = P.kx;
   const double *__restrict__ ky = P.ky;
   double *__restrict__ r = P.r;
@@ -430,12 +427,12 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(cons
       tl_reflect_edges(sout, g, m, j, oc, last ? Xc : sn);
       // tiled: the next inner step reads the neighbours' sd'; after the last step the next
       // outer iteration's matvec reads their r (p = r + beta p is recomputed at the neighbours)
-      if (tiled) pushed |= last ? tl_push_edges(P.push_r, g, m, j, rn) : tl_push_edges(push, g, m, j, sn);
+      if (tiled) tl_push_edges(last ? P.push_r : push, g, m, j, last ? rn : sn);
       Xm = Xc; Xc = Xn; XcE = cur.xe; kyc = cur.ky;
     }
     tl_cp_wait<0>();
   }
-  if (tl_kernel_tail(acc, last, pushed, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, last, st, P.partials, P.cd, sm)) {
     if (last) {
       st->red_rr_local = acc[0];      // PPCG.jl:88
       if (P.single || tiled) st->red_rr = acc[0];
