@@ -128,6 +128,10 @@ int tl_ppcg_init_sd(tl_ctx *ctx, double theta);
 /* the inner loop of PPCG.mainstep!, src/solvers/PPCG.jl:75-84: nsteps x
  * { halo(sd); r -= A sd; u += sd; sd = alphas[pp] sd + betas[pp] r } (two-phase). */
 int tl_ppcg_inner(tl_ctx *ctx, const double *alphas, const double *betas, int nsteps);
+/* Jacobi.init!, src/solvers/Jacobi.jl:33-60 */
+int tl_jacobi_init(tl_ctx *ctx, int coefficient, double rx, double ry);
+/* Jacobi.iterate!, src/solvers/Jacobi.jl:62-82 -> sum(|u - r|) */
+int tl_jacobi_iterate(tl_ctx *ctx, double *error);
 /* fieldsummary, src/kernels.jl:119-133: temp = sum(volume*density*u); vol, mass, ie are
  * the upstream companions named by the parity criterion. */
 int tl_field_summary(tl_ctx *ctx, double cell_volume, double *vol, double *mass, double *ie, double *temp);
@@ -143,6 +147,10 @@ int tl_cheby_solve(tl_ctx *ctx, int coefficient, double rx, double ry, double ep
 /* PPCG.solve!, src/solvers/PPCG.jl:9-55 */
 int tl_ppcg_solve(tl_ctx *ctx, int coefficient, double rx, double ry, double eps, int max_iters,
                   int presteps, double epslim, int errorswitch, int inner_steps, tl_solve_info *info);
+
+/* Jacobi.driver! -- the module's solve!, src/solvers/Jacobi.jl:7-31 */
+int tl_jacobi_solve(tl_ctx *ctx, int coefficient, double rx, double ry, double eps, int max_iters,
+                    tl_solve_info *info);
 
 /* ---- measurement helpers (bench.py) -------------------------------------------- */
 /* average device time (ms) of the named fused kernel over `reps` launches on the current

@@ -183,6 +183,22 @@ function solve!(chunk::B200Chunk, set::Settings, rx::Float64, ry::Float64)
 end
 end # module PPCG
 
+module Jacobi
+using ..TeaLeafB200: B200Chunk, SolveInfo, LIB, check
+using TeaLeaf
+"Jacobi.driver! under the name `diffuse!` dispatches on (src/TeaLeaf.jl:74), src/solvers/Jacobi.jl:7-31"
+function solve!(chunk::B200Chunk, set::Settings, rx::Float64, ry::Float64)::Float64
+    info = Ref{SolveInfo}()
+    check(chunk, ccall((:tl_jacobi_solve, LIB), Cint,
+                       (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cdouble, Cint, Ref{SolveInfo}),
+                       chunk.ctx, set.coefficient, rx, ry, set.eps, set.maxiters, info))
+    resettoexchange!(set); set.toexchange[:u] = true
+    final_time = info[].iters
+    @info "Jacobi" final_time
+    return info[].error
+end
+end # module Jacobi
+
 # ---- per-kernel entry points, for a host that keeps solve! written in Julia ---------------------
 # (same names and argument order as src/solvers/CG.jl; used by TeaLeaf.CG.mainstep! unchanged)
 function TeaLeaf.CG.init!(chunk::B200Chunk, hd::Int, coef::Int, rx::Float64, ry::Float64)

@@ -209,3 +209,37 @@ class Twin:
             if abs(error) < eps:
                 break
         return {"iters": tt, "cg_iters": cgiters, "cheby_iters": ppcgiters, "error": error}
+
+    # -- src/solvers/Jacobi.jl:7-82 (A#21) --
+    def jacobi_solve(self, rx, ry, eps, maxiters):
+        hd, x, y = self.hd, self.x, self.y
+        self.u = self.energy * self.density
+        self.u0 = self.u.copy()
+        d = self.density if self.coef == 1 else 1.0 / self.density
+        dc, dl, dd = d[hd:x - 1, hd:y - 1], d[hd - 1:x - 2, hd:y - 1], d[hd:x - 1, hd - 1:y - 2]
+        self.kx[hd:x - 1, hd:y - 1] = rx * (dl + dc) / (2.0 * dl * dc)
+        self.ky[hd:x - 1, hd:y - 1] = ry * (dd + dc) / (2.0 * dd * dc)
+        c = self.I
+        xr = (slice(hd + 1, x - hd + 1), slice(hd, y - hd))
+        xl = (slice(hd - 1, x - hd - 1), slice(hd, y - hd))
+        yu = (slice(hd, x - hd), slice(hd + 1, y - hd + 1))
+        yd = (slice(hd, x - hd), slice(hd - 1, y - hd - 1))
+        kx, ky = self.kx, self.ky
+        error, iters = ERROR_START, 0
+        for tt in range(1, maxiters + 1):
+            iters = tt
+            self.r = self.u.copy()
+            r = self.r
+            num = (((self.u0[c] + kx[xr] * r[xr]) + kx[c] * r[xl]) + ky[yu] * r[yu]) + ky[c] * r[yd]
+            den = (((1.0 + kx[c]) + kx[xr]) + ky[c]) + ky[yu]
+            self.u[c] = num / den
+            error = float(np.abs(self.u[c] - r[c]).sum())
+            if tt % 50 == 0:
+                self.halo(self.u)
+                self.r[c] = self.u0[c] - self.smvp(self.u)
+                error = float((self.r[c] ** 2).sum())
+            self.halo(self.u)
+            if abs(error) < eps:
+                break
+        return {"iters": iters, "error": error}
+

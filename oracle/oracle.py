@@ -66,6 +66,8 @@ def load():
             "tlo_cg_solve": (None, [P, I, D, D, D, I, C.POINTER(Result)]),
             "tlo_cheby_solve": (None, [P, I, D, D, D, I, I, D, I, C.POINTER(Result)]),
             "tlo_ppcg_solve": (None, [P, I, D, D, D, I, I, D, I, I, C.POINTER(Result)]),
+            "tlo_jacobi_init": (None, [P, I, D, D, C.POINTER(I)]), "tlo_jacobi_iterate": (D, [P]),
+            "tlo_jacobi_solve": (None, [P, I, D, D, D, I, C.POINTER(Result)]),
             "tlo_solve_finished": (None, [P, I]),
             "tlo_cg_fixed_iters": (D, [P, D, I]),
         }
@@ -213,6 +215,20 @@ class OracleChunk:
         r = Result()
         self._l.tlo_ppcg_solve(self.c, s.coefficient, rx, ry, s.eps, s.maxiters, s.presteps, s.epslim,
                                int(s.errorswitch), s.ppcginnersteps, C.byref(r))
+        return self._res(r)
+
+    def jacobi_init(self, coef, rx, ry):
+        st = C.c_int()
+        self._l.tlo_jacobi_init(self.c, coef, rx, ry, C.byref(st))
+        if st.value:
+            raise ValueError(f"Coefficient {coef} is not valid")
+
+    def jacobi_iterate(self):
+        return self._l.tlo_jacobi_iterate(self.c)
+
+    def jacobi_solve(self, s, rx, ry):
+        r = Result()
+        self._l.tlo_jacobi_solve(self.c, s.coefficient, rx, ry, s.eps, s.maxiters, C.byref(r))
         return self._res(r)
 
     def cg_fixed_iters(self, rro, iters):

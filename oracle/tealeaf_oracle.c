@@ -569,6 +569,72 @@ void tlo_ppcg_solve(tlo_chunk *c, int coef, double rx, double ry, double eps, in
   res->eigmin = c->eigmin; res->eigmax = c->eigmax;
 }
 
+/* ------------------------------------------------------------------ */
+/* Jacobi (src/solvers/Jacobi.jl) -- SURVEY.md section 8(f) item 1, A#21.     */
+/* ------------------------------------------------------------------ */
+/* src/solvers/Jacobi.jl:33-60.  *status = -1 on an invalid coefficient (:34-36, as written:
+ * only values below min(CONDUCTIVITY, RECIP_CONDUCTIVITY) are rejected). */
+void tlo_jacobi_init(tlo_chunk *c, int coef, double rx, double ry, int *status) {
+  int x = c->x, y = c->y, hd = c->hd;
+  double *u = c->f[F_U], *u0 = c->f[F_U0], *kx = c->f[F_KX], *ky = c->f[F_KY];
+  const double *energy = c->f[F_ENERGY], *density = c->f[F_DENSITY];
+  if (status) *status = 0;
+  if (coef < TLO_CONDUCTIVITY) { if (status) *status = -1; return; }
+  size_t n = (size_t)x * y;
+  for (size_t i = 0; i < n; i++) { double t = energy[i] * density[i]; u0[i] = t; u[i] = t; }   /* :39-41 */
+  /* :43-51  jj = hd+1:y-1, kk = hd+1:x-1 (1-based); density^p with p = +-1 (x^-1 == inv(x)) */
+  for (int j = hd; j < y - 1; j++)
+    for (int k = hd; k < x - 1; k++) {
+      double dc = density[IDX(c, k, j)], dl = density[IDX(c, k - 1, j)], dd = density[IDX(c, k, j - 1)];
+      if (coef != TLO_CONDUCTIVITY) { dc = 1.0 / dc; dl = 1.0 / dl; dd = 1.0 / dd; }
+      kx[IDX(c, k, j)] = rx * (dl + dc) / (2.0 * dl * dc);
+      ky[IDX(c, k, j)] = ry * (dd + dc) / (2.0 * dd * dc);
+    }
+  tlo_copy_u(c);   /* :53 */
+}
+
+/* src/solvers/Jacobi.jl:62-82: r .= u (whole array), Jacobi sweep on the interior, returns
+ * sum(|u - r|) (halo cells contribute 0: r is a copy of u there). */
+double tlo_jacobi_iterate(tlo_chunk *c) {
+  int x = c->x, y = c->y, hd = c->hd;
+  double *u = c->f[F_U], *r = c->f[F_R];
+  const double *u0 = c->f[F_U0], *kx = c->f[F_KX], *ky = c->f[F_KY];
+  memcpy(r, u, (size_t)x * y * sizeof(double));
+  double err = 0.0;
+#pragma omp parallel for reduction(+ : err) if (c->nthreads > 1)
+  for (int j = hd; j < y - hd; j++)
+    for (int k = hd; k < x - hd; k++) {
+      size_t i = IDX(c, k, j);
+      double num = (((u0[i] + kx[IDX(c, k + 1, j)] * r[IDX(c, k + 1, j)]) + kx[i] * r[IDX(c, k - 1, j)]) +
+                    ky[IDX(c, k, j + 1)] * r[IDX(c, k, j + 1)]) + ky[i] * r[IDX(c, k, j - 1)];
+      double den = (((1.0 + kx[i]) + kx[IDX(c, k + 1, j)]) + ky[i]) + ky[IDX(c, k, j + 1)];
+      u[i] = num / den;
+      err += fabs(u[i] - r[i]);
+    }
+  return err;
+}
+
+/* src/solvers/Jacobi.jl:7-31 with A#21 (entry point renamed solve!, `error +=` read as `=`). */
+void tlo_jacobi_solve(tlo_chunk *c, int coef, double rx, double ry, double eps, int max_iters, tlo_result *res) {
+  memset(res, 0, sizeof(*res));
+  tlo_jacobi_init(c, coef, rx, ry, &res->status);
+  if (res->status) return;
+  double error = TLO_ERROR_START;
+  if (max_iters > c->max_iters) max_iters = c->max_iters;
+  for (int tt = 1; tt <= max_iters; tt++) {
+    res->iters = tt;
+    error = tlo_jacobi_iterate(c);             /* :14 */
+    if (tt % 50 == 0) {                        /* :16-21 */
+      tlo_halo_update(c, 1u << F_U, 1);
+      tlo_calc_residual(c);
+      error = tlo_norm2(c, F_R);
+    }
+    tlo_halo_update(c, 1u << F_U, 1);          /* :23 sticky {u} */
+    if (fabs(error) < eps) break;              /* :26 */
+  }
+  res->error = error;
+}
+
 /* src/kernels.jl:166-170 */
 void tlo_solve_finished(tlo_chunk *c, int check_result) {
   if (check_result) tlo_calc_residual(c);

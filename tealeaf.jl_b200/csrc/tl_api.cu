@@ -92,8 +92,8 @@ struct tl_ctx {
   int l2_persist_field = TL_R;
   Tiling tiling{}, pw_tiling{};   // stencil kernels / pointwise kernels
   int fused_grid = 0, pw_grid = 0, basic_grid = 0;
-  cudaGraphExec_t g_cg = nullptr, g_cheby = nullptr, g_ppcg = nullptr;
-  int g_cg_iters = 0, g_cheby_iters = 0, g_ppcg_iters = 0, g_ppcg_inner = 0;
+  cudaGraphExec_t g_cg = nullptr, g_cheby = nullptr, g_ppcg = nullptr, g_jacobi = nullptr;
+  int g_cg_iters = 0, g_cheby_iters = 0, g_ppcg_iters = 0, g_ppcg_inner = 0, g_jacobi_iters = 0;
   long long launches = 0;
   // peers (tile-internal sides): 0 left, 1 right, 2 bottom, 3 top
   int nbr_rank[4] = {-1, -1, -1, -1};
@@ -154,8 +154,14 @@ static void compute_tiling(tl_ctx *c) {
   const long cells_tile = (long)g.nx * g.ny;
   c->ring_eff = c->ring_stages >= 0 ? c->ring_stages : (cells_tile >= (long)8192 * 8192 ? 4 : 3);
   const int bps = (c->ring_eff == 3) ? 3 : (c->ring_eff == 4) ? 2 : 1;   // the kernels' launch bounds
-  const int cr = c->chunk_rows >= 0 ? c->chunk_rows : 8;
-  const int pcr = c->pw_chunk_rows >= 0 ? c->pw_chunk_rows : 16;
+  // rows per warp: 8 (stencil) / 16 (pointwise) once the mesh fills the machine; small meshes get
+  // shorter chunks so that at least half a wave of warps exists (profiles/r01c_small_mesh_sweep.log)
+  const long warp_rows = (long)((g.nx + TL_STRIP - 1) / TL_STRIP) * g.ny;
+  int cr = (int)std::min<long>(8, std::max<long>(1, warp_rows / ((long)c->num_sms * bps * 4)));
+  int pcr = (int)std::min<long>(16, std::max<long>(1, warp_rows / ((long)c->num_sms * c->pw_blocks_per_sm * 4)));
+  if (pcr >= 4) pcr &= ~3;   // the pointwise kernels are unrolled by 4 rows
+  if (c->chunk_rows >= 0) cr = c->chunk_rows;
+  if (c->pw_chunk_rows >= 0) pcr = c->pw_chunk_rows;
   make_tiling(c, bps, cr, &c->tiling, &c->fused_grid);
   make_tiling(c, c->pw_blocks_per_sm, pcr, &c->pw_tiling, &c->pw_grid);
   const long cells = (long)(g.nx + 2 * g.hd) * (g.ny + 2 * g.hd);
@@ -198,6 +204,7 @@ static void destroy_graphs(tl_ctx *c) {
   if (c->g_cg) { cudaGraphExecDestroy(c->g_cg); c->g_cg = nullptr; }
   if (c->g_cheby) { cudaGraphExecDestroy(c->g_cheby); c->g_cheby = nullptr; }
   if (c->g_ppcg) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
+  if (c->g_jacobi) { cudaGraphExecDestroy(c->g_jacobi); c->g_jacobi = nullptr; }
 }
 
 extern "C" int tl_abi_version(void) { return TL_ABI_VERSION; }
@@ -1212,6 +1219,116 @@ extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double e
   info->inner_total = info->cheby_iters * inner_steps;
   info->iters = fin.iter;
   info->error = fin.red_rr;
+  return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Jacobi (src/solvers/Jacobi.jl)
+// ---------------------------------------------------------------------------------------
+static int jacobi_init_async(tl_ctx *c, int coef, double rx, double ry) {
+  if (coef < TL_CONDUCTIVITY) return tl_fail(c, TL_ERR_ARG, "Coefficient %d is not valid.", coef);  // Jacobi.jl:34-36
+  c->p_cur = c->u_cur = c->sd_cur = 0;
+  LAUNCH_BASIC(c, k_jacobi_init_fields, c->g, c->buf[TL_ENERGY], c->buf[TL_DENSITY], c->buf[TL_U], c->buf[TL_U0]);
+  LAUNCH_BASIC(c, k_jacobi_init_k, c->g, coef, rx, ry, c->buf[TL_DENSITY], c->buf[TL_KX], c->buf[TL_KY]);
+  return TL_OK;   // copyu! (Jacobi.jl:53) is the identity after u0 .= u
+}
+
+extern "C" int tl_jacobi_init(tl_ctx *c, int coef, double rx, double ry) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  TRY(jacobi_init_async(c, coef, rx, ry));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
+extern "C" int tl_jacobi_iterate(tl_ctx *c, double *error) {
+  if (!c) return TL_ERR_ARG;
+  CU(c, cudaSetDevice(c->device));
+  LAUNCH_BASIC(c, k_copy, c->g, 1, field_ptr(c, TL_U), c->buf[TL_R]);          // Jacobi.jl:64  r .= u
+  LAUNCH_BASIC(c, k_jacobi_sweep, c->g, c->buf[TL_U0], c->buf[TL_KX], c->buf[TL_KY], c->buf[TL_R], field_ptr(c, TL_U),
+               c->partials, &c->st->counter, &c->st->red_aux[0]);
+  TRY(allreduce(c, &c->st->red_aux[0], 1));
+  double v;
+  TRY(read_scalars(c, &c->st->red_aux[0], 1, &v));
+  if (error) *error = v;
+  return TL_OK;
+}
+
+static JacobiParams jacobi_params(tl_ctx *c, int force_resid) {
+  JacobiParams P;
+  P.g = c->g; P.t = c->tiling; P.st = c->st;
+  P.u0 = c->buf[TL_U0]; P.ua = c->buf[TL_U]; P.ub = c->buf[B_U1]; P.r = c->buf[TL_R];
+  P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
+  P.single = c->nranks == 1; P.force_resid = force_resid;
+  P.cd = comm_dev(c); P.push_ua = push_for(c, TL_U); P.push_ub = push_for(c, B_U1);
+  return P;
+}
+template <int S, int MINB>
+static int launch_jacobi_ring(tl_ctx *c, const JacobiParams &P) {
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(c, cudaFuncSetAttribute(k_jacobi_fused_ring<S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  k_jacobi_fused_ring<S, MINB><<<c->fused_grid, TL_FUSED_THREADS, smem, c->stream>>>(P);
+  return TL_OK;
+}
+static int launch_jacobi(tl_ctx *c) {
+  const JacobiParams P = jacobi_params(c, 0);
+  switch (c->ring_eff) {
+    case 3: TRY((launch_jacobi_ring<3, 3>(c, P))); break;
+    case 4: TRY((launch_jacobi_ring<4, 2>(c, P))); break;
+    case 6: TRY((launch_jacobi_ring<6, 1>(c, P))); break;
+    default: return tl_fail(c, TL_ERR_STATE, "internal: ring depth %d", c->ring_eff);
+  }
+  CHECK_LAUNCH(c);
+  c->launches++;
+  return TL_OK;
+}
+static int launch_jacobi_resid(tl_ctx *c, int force) {
+  k_jacobi_resid<<<c->basic_grid, TL_BASIC_THREADS, 0, c->stream>>>(jacobi_params(c, force));
+  CHECK_LAUNCH(c);
+  c->launches++;
+  return TL_OK;
+}
+
+// Jacobi.driver! (the module's solve!), src/solvers/Jacobi.jl:7-31.
+// A graph holds 50 iteration kernels followed by the residual kernel of Jacobi.jl:16-21.
+extern "C" int tl_jacobi_solve(tl_ctx *c, int coef, double rx, double ry, double eps, int max_iters, tl_solve_info *info) {
+  if (!c || !info) return TL_ERR_ARG;
+  memset(info, 0, sizeof *info);
+  CU(c, cudaSetDevice(c->device));
+  if (legacy_comm(c)) return tl_fail(c, TL_ERR_STATE, "tl_jacobi_solve on tiles needs comm_fused = 1");
+  max_iters = std::min(max_iters, c->max_iters);
+  const long long l0 = c->launches;
+  CU(c, cudaEventRecord(c->ev_start, c->stream));
+  TRY(jacobi_init_async(c, coef, rx, ry));
+  LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[TL_U], c->buf[B_U1]);    // both u buffers agree in the deep halos
+  StopCfg cfg{max_iters, TL_CONV_ABS, INT_MAX, 0, eps, 0.0};
+  k_state_begin<<<1, 1, 0, c->stream>>>(c->st, cfg, 0, 0.0, 0);
+  c->launches++;
+  CHECK_LAUNCH(c);
+  if (c->nranks > 1) TRY(tile_barrier(c));   // the first kernel pushes into the neighbours' B_U1 halos
+  const long long saved = c->launches;
+  auto enq = [&]() -> int {
+    for (int i = 0; i < 50; i++) TRY(launch_jacobi(c));
+    return launch_jacobi_resid(c, 0);
+  };
+  auto stop = [&](const SolveState &s) { return tl_should_stop(s.iter, s.red_rr, s.cfg); };
+  SolveState fin;
+  TRY(run_chunks(c, &c->g_jacobi, &c->g_jacobi_iters, 1, 51, enq, stop, &fin));
+  (void)saved;
+  // leave the reference's post-solve state: u in its own buffer, r = the previous iterate
+  // (Jacobi.jl:64) or, after a 50th iteration, the residual on the interior
+  const int cur = fin.iter & 1;
+  LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[cur ? TL_U : B_U1], c->buf[TL_R]);
+  if (fin.iter > 0 && fin.iter % 50 == 0) TRY(launch_jacobi_resid(c, 1));
+  if (cur) LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[B_U1], c->buf[TL_U]);
+  c->u_cur = 0;
+  finish_timing(c, info, l0);
+  info->iters = fin.iter;
+  info->error = fin.iter > 0 ? fin.red_rr : TL_ERROR_START;
   return TL_OK;
 }
 

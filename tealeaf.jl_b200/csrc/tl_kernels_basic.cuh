@@ -187,6 +187,50 @@ __global__ void k_ppcg_inner2(Geo g, double alpha, double beta, const double *__
   }
 }
 
+// ---- Jacobi (src/solvers/Jacobi.jl) ----------------------------
+// Jacobi.jl:39-41: u0 = u = energy .* density on the whole array
+__global__ void k_jacobi_init_fields(Geo g, const double *__restrict__ energy, const double *__restrict__ density,
+                                     double *u, double *u0) {
+  TL_RECT_LOOP(-g.hd, g.nx + g.hd, -g.hd, g.ny + g.hd) {
+    const long o = (long)j * g.pitch + i;
+    const double t = energy[o] * density[o];
+    u0[o] = t;
+    u[o] = t;
+  }
+}
+// Jacobi.jl:43-51: jj = hd+1:y-1, kk = hd+1:x-1; density^p, p = +-1
+__global__ void k_jacobi_init_k(Geo g, int coef, double rx, double ry, const double *__restrict__ density, double *kx,
+                                double *ky) {
+  TL_RECT_LOOP(0, g.nx + g.hd - 1, 0, g.ny + g.hd - 1) {
+    const long o = (long)j * g.pitch + i;
+    double dc = density[o], dl = density[o - 1], dd = density[o - g.pitch];
+    if (coef != 1) { dc = 1.0 / dc; dl = 1.0 / dl; dd = 1.0 / dd; }
+    kx[o] = rx * (dl + dc) / (2.0 * dl * dc);
+    ky[o] = ry * (dd + dc) / (2.0 * dd * dc);
+  }
+}
+// the sweep of Jacobi.iterate!, Jacobi.jl:65-80 (r holds the previous u), -> sum |u - r|
+__device__ __forceinline__ double tl_jacobi_cell(double u0, double kxl, double kxr, double kyd, double kyu, double xl,
+                                                 double xr, double xd, double xu) {
+  const double num = (((u0 + kxr * xr) + kxl * xl) + kyu * xu) + kyd * xd;
+  const double den = (((1.0 + kxl) + kxr) + kyd) + kyu;
+  return num / den;
+}
+__global__ void k_jacobi_sweep(Geo g, const double *__restrict__ u0, const double *__restrict__ kx,
+                               const double *__restrict__ ky, const double *__restrict__ r, double *u, double *partials,
+                               unsigned *counter, double *out) {
+  __shared__ double sm[32];
+  double acc[1] = {0.0};
+  TL_RECT_LOOP(0, g.nx, 0, g.ny) {
+    const long o = (long)j * g.pitch + i;
+    const double un = tl_jacobi_cell(u0[o], kx[o], kx[o + 1], ky[o], ky[o + g.pitch], r[o - 1], r[o + 1], r[o - g.pitch],
+                                     r[o + g.pitch]);
+    u[o] = un;
+    acc[0] += fabs(un - r[o]);
+  }
+  if (tl_grid_sum<1>(acc, partials, counter, sm) && threadIdx.x == 0) *out = acc[0];
+}
+
 // kernels.jl:191-210 with the 1-based reflection of Appendix A #2.  Only sides flagged
 // physical in g.phys are reflected (tile-internal sides are filled by k_pull_halo).
 // x faces run over interior rows, y faces over interior columns -- corners are not touched,

@@ -312,3 +312,23 @@ struct PpcgInnerParams {
   const CommDev *cd;
   Push push_sda, push_sdb, push_r;
 };
+
+// ------------------------------------------------------------------------------------------
+// Jacobi iteration, one kernel (k_jacobi_fused_ring):  r .= u ; u = (u0 + sum k*r_nbr) / diag ;
+// error = sum |u - r|  (Jacobi.iterate!, Jacobi.jl:62-82).  u is ping-ponged, so the buffer read
+// IS the reference's r.  HBM traffic per cell: read u, u0, kx, ky; write u' = 40 B
+// (as written: 72 B).  Every 50th iteration k_jacobi_resid replaces the error by sum(r.r) of the
+// true residual (Jacobi.jl:16-21).
+// ------------------------------------------------------------------------------------------
+struct JacobiParams {
+  Geo g; Tiling t;
+  SolveState *st;
+  const double *u0; double *ua; double *ub; double *r;
+  const double *kx; const double *ky;
+  double *partials;
+  int single;
+  int force_resid;   // k_jacobi_resid: run whatever the iteration number is
+  const CommDev *cd;
+  Push push_ua, push_ub;
+};
+

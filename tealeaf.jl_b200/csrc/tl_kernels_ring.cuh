@@ -11,6 +11,7 @@
 // (S-1) x 2.5 KB per warp in flight (vs 2.5 KB with register double-buffering), which is what an
 // HBM3e stack at ~1 us loaded latency needs (Little: 6.5 TB/s x 1 us = 6.5 MB chip-wide).
 #pragma once
+#include "tl_kernels_basic.cuh"
 #include "tl_kernels_fused.cuh"
 
 #define TL_RING_FIELDS 5
@@ -441,3 +442,109 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(cons
     st->inner_pp = pp + 1;
   }
 }
+
+// Jacobi iteration (algorithm and citations: JacobiParams in tl_kernels_fused.cuh).
+template <int S, int MINB>
+__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_jacobi_fused_ring(const JacobiParams P) {
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  __shared__ double sm[32];
+  SolveState *st = P.st;
+  const int it = st->iter;
+  if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
+  const double *__restrict__ uin = (it & 1) ? P.ub : P.ua;
+  double *__restrict__ uout = (it & 1) ? P.ua : P.ub;
+  const bool tiled = P.cd != nullptr;
+  const Push &push = (it & 1) ? P.push_ua : P.push_ub;   // halo targets of uout
+  const double *__restrict__ u0 = P.u0;
+  const double *__restrict__ kx = P.kx;
+  const double *__restrict__ ky = P.ky;
+  const Geo g = P.g;
+  const int pitch = g.pitch;
+  const bool physL = g.phys & TL_PHYS_LEFT, physR = g.phys & TL_PHYS_RIGHT;
+  const bool physB = g.phys & TL_PHYS_BOTTOM, physT = g.phys & TL_PHYS_TOP;
+
+  double acc[1] = {0.0};
+  MarchCtx m;
+  if (tl_march_setup(g, P.t, m)) {
+    const double2 z2 = make_double2(0.0, 0.0);
+    RingMarch<S> rg;
+    rg.init(ring_raw, m);
+    double2 Xm, Xc, kyc;
+    double XcE;
+    {
+      const int jm = (m.j0 == 0 && physB) ? 0 : m.j0 - 1;
+      const long om = (long)jm * pitch + m.i0, oc = (long)m.j0 * pitch + m.i0;
+      Xm = m.ld_ok ? tl_ld2(uin + om) : z2;
+      Xc = m.ld_ok ? tl_ld2(uin + oc) : z2;
+      kyc = m.ld_ok ? tl_ld2(ky + oc) : z2;
+      XcE = m.has_edge ? __ldg(uin + (long)m.j0 * pitch + m.ecol) : 0.0;
+    }
+#pragma unroll
+    for (int d = 0; d < S - 1; d++) {
+      if (m.j0 + d < m.j1) rg.issue(g, m, physT, m.j0 + d, d, uin, ky, kx, u0, nullptr);
+      tl_cp_commit();
+    }
+    for (int j = m.j0; j < m.j1; j++) {
+      if (j + S - 1 < m.j1) rg.issue(g, m, physT, j + S - 1, rg.fill, uin, ky, kx, u0, nullptr);
+      tl_cp_commit();
+      tl_cp_wait<S - 1>();
+      const RingRow cur = rg.take(m, true, false);
+      const double2 Xn = cur.x;
+      double xl = __shfl_up_sync(0xffffffffu, Xc.y, 1);
+      double xr = __shfl_down_sync(0xffffffffu, Xc.x, 1);
+      double kxr = __shfl_down_sync(0xffffffffu, cur.kx.x, 1);
+      if (m.lane == 0) xl = XcE;
+      if (m.lane == 31) { xr = XcE; kxr = cur.kxe; }
+      const double La = (physL && m.i0 == 0) ? Xc.x : xl;
+      const double Ra = (physR && m.i0 == g.nx - 1) ? Xc.x : Xc.y;
+      const double Lb = Xc.x;
+      const double Rb = (physR && m.i0 + 1 == g.nx - 1) ? Xc.y : xr;
+      double2 un;
+      un.x = tl_jacobi_cell(cur.a.x, cur.kx.x, cur.kx.y, kyc.x, cur.ky.x, La, Ra, Xm.x, Xn.x);
+      un.y = tl_jacobi_cell(cur.a.y, cur.kx.y, kxr, kyc.y, cur.ky.y, Lb, Rb, Xm.y, Xn.y);
+      const long oc = (long)j * pitch + m.i0;
+      if (m.actb) {
+        tl_st2(uout + oc, un);
+        acc[0] += fabs(un.x - Xc.x);
+        acc[0] += fabs(un.y - Xc.y);
+      } else if (m.acta) {
+        uout[oc] = un.x;
+        acc[0] += fabs(un.x - Xc.x);
+      }
+      tl_reflect_edges(uout, g, m, j, oc, un);             // haloupdate!(.., [:u]) Jacobi.jl:23
+      if (tiled) tl_push_edges(push, g, m, j, un);
+      Xm = Xc; Xc = Xn; XcE = cur.xe; kyc = cur.ky;
+    }
+    tl_cp_wait<0>();
+  }
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
+    st->red_rr_local = acc[0];
+    st->red_rr = acc[0];
+    st->iter = it + 1;
+  }
+}
+
+// Jacobi.jl:16-21: on every 50th iteration  r = u0 - A u ; error = sum(r.r).  Runs after the
+// iteration kernel (whose tail exchange completed the halo pushes of u); idempotent, so the
+// launched-ahead copies after the stop rule fired leave the state unchanged.
+__global__ void __launch_bounds__(TL_BASIC_THREADS) k_jacobi_resid(const JacobiParams P) {
+  __shared__ double sm[32];
+  SolveState *st = P.st;
+  const int it = st->iter;
+  if (st->comm_error) return;
+  if (!P.force_resid && (it == 0 || it % 50 != 0)) return;
+  const double *__restrict__ u = (it & 1) ? P.ub : P.ua;
+  const Geo g = P.g;
+  double acc[1] = {0.0};
+  TL_RECT_LOOP(0, g.nx, 0, g.ny) {
+    const long o = (long)j * g.pitch + i;
+    const double rv = P.u0[o] - tl_smvp(u, P.kx, P.ky, o, g.pitch);
+    P.r[o] = rv;
+    acc[0] += rv * rv;
+  }
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
+    st->red_rr_local = acc[0];
+    if (!P.force_resid) st->red_rr = acc[0];
+  }
+}
+

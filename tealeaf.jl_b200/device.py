@@ -151,6 +151,14 @@ class DeviceChunk:
         self._ck(self._l.tl_ppcg_inner(self.ctx, a.ctypes.data_as(C.POINTER(C.c_double)),
                                        b.ctypes.data_as(C.POINTER(C.c_double)), nsteps))
 
+    def jacobi_init(self, coef: int, rx: float, ry: float):
+        self._ck(self._l.tl_jacobi_init(self.ctx, coef, rx, ry))
+
+    def jacobi_iterate(self) -> float:
+        out = C.c_double()
+        self._ck(self._l.tl_jacobi_iterate(self.ctx, C.byref(out)))
+        return out.value
+
     def fieldsummary(self, cell_volume: float):
         v = [C.c_double() for _ in range(4)]
         self._ck(self._l.tl_field_summary(self.ctx, cell_volume, *[C.byref(q) for q in v]))
@@ -174,6 +182,12 @@ class DeviceChunk:
         info = _lib.SolveInfo()
         self._ck(self._l.tl_ppcg_solve(self.ctx, s.coefficient, rx, ry, s.eps, min(s.maxiters, self.maxiters),
                                        s.presteps, s.epslim, int(s.errorswitch), s.ppcginnersteps, C.byref(info)))
+        return info.as_dict()
+
+    def jacobi_solve(self, s: Settings, rx: float, ry: float) -> dict:
+        info = _lib.SolveInfo()
+        self._ck(self._l.tl_jacobi_solve(self.ctx, s.coefficient, rx, ry, s.eps, min(s.maxiters, self.maxiters),
+                                         C.byref(info)))
         return info.as_dict()
 
     def time_kernel(self, kernel: str, reps: int = 20) -> float:

@@ -68,10 +68,13 @@ SIGNATURES = {
     "tl_cheby_iterate": (_I, [_P, _D, _D, _I, _DP]),
     "tl_ppcg_init_sd": (_I, [_P, _D]),
     "tl_ppcg_inner": (_I, [_P, _DP, _DP, _I]),
+    "tl_jacobi_init": (_I, [_P, _I, _D, _D]),
+    "tl_jacobi_iterate": (_I, [_P, _DP]),
     "tl_field_summary": (_I, [_P, _D, _DP, _DP, _DP, _DP]),
     "tl_cg_solve": (_I, [_P, _I, _D, _D, _D, _I, C.POINTER(SolveInfo), _DP, _DP]),
     "tl_cheby_solve": (_I, [_P, _I, _D, _D, _D, _I, _I, _D, _I, C.POINTER(SolveInfo)]),
     "tl_ppcg_solve": (_I, [_P, _I, _D, _D, _D, _I, _I, _D, _I, _I, C.POINTER(SolveInfo)]),
+    "tl_jacobi_solve": (_I, [_P, _I, _D, _D, _D, _I, C.POINTER(SolveInfo)]),
     "tl_time_kernel": (_I, [_P, C.c_char_p, _I, _DP]),
     "tl_timer_start": (_I, [_P]),
     "tl_timer_stop": (_I, [_P, _DP]),

@@ -1,4 +1,4 @@
-"""Solver modules -- host-side mirror of `src/solvers/{CG,Cheby,PPCG}.jl`.
+"""Solver modules -- host-side mirror of `src/solvers/{CG,Cheby,PPCG,Jacobi}.jl`.
 
 Two ways to run a solve, both behind the reference's entry point
 `settings.solver.solve!(chunk, settings, rx, ry)` (src/TeaLeaf.jl:74):
@@ -247,7 +247,42 @@ class PPCG:
         return info
 
 
-SOLVER_MODULES = {"cg": CG, "cheby": Cheby, "ppcg": PPCG}
+# ------------------------------------------------------------------------------------------
+# Jacobi  
+# ------------------------------------------------------------------------------------------
+class Jacobi:
+    name = "jacobi"
+
+    @staticmethod
+    def solve_stepwise(chunk, settings: Settings, rx: float, ry: float) -> dict:
+        """`Jacobi.driver!`, src/solvers/Jacobi.jl:7-31 (A#21: it is the module's `solve!`, and
+        `error +=` is read as `error =`)."""
+        chunk.jacobi_init(settings.coefficient, rx, ry)     # Jacobi.jl:8
+        resettoexchange(settings)
+        settings.toexchange["u"] = True                     # Jacobi.jl:55-56
+        error = ERROR_START
+        iters = 0
+        for tt in range(1, settings.maxiters + 1):
+            iters = tt
+            error = chunk.jacobi_iterate()                  # Jacobi.jl:14
+            if tt % 50 == 0:                                # Jacobi.jl:16-21
+                haloupdate(chunk, settings, 1)
+                chunk.residual()
+                error = chunk.norm2("r")
+            haloupdate(chunk, settings, 1)                  # Jacobi.jl:23
+            if abs(error) < settings.eps:                   # Jacobi.jl:26
+                break
+        return {"iters": iters, "cg_iters": 0, "error": error}
+
+    @staticmethod
+    def solve(chunk, settings: Settings, rx: float, ry: float) -> dict:
+        info = chunk.jacobi_solve(settings, rx, ry)
+        resettoexchange(settings)
+        settings.toexchange["u"] = True
+        return info
+
+
+SOLVER_MODULES = {"cg": CG, "cheby": Cheby, "ppcg": PPCG, "jacobi": Jacobi}
 
 
 def get_solver(name: str):

@@ -27,6 +27,7 @@ def main():
     cases = [("cg", 256, 192, 2, {}, 1), ("cg", 130, 77, 1, {}, 1), ("cheby", 192, 256, 1, {}, 1),
              ("ppcg", 192, 160, 1, {"ppcginnersteps": 6}, 1), ("ppcg", 131, 150, 1, {"ppcginnersteps": 5}, 1),
              ("cheby", 129, 67, 1, {}, 1), ("cg", 512, 512, 1, {"maxiters": 300}, 1),
+             ("jacobi", 160, 130, 1, {"maxiters": 120}, 1),
              # the older halo-pull + NCCL path (comm_fused = 0) stays available for A/B measurements
              ("cg", 256, 192, 1, {}, 0), ("cheby", 192, 256, 1, {}, 0), ("ppcg", 192, 160, 1, {"ppcginnersteps": 6}, 0)]
     if len(sys.argv) > 1:

@@ -194,6 +194,61 @@ def test_fused_ppcg_matches_oracle(nx, ny, inner):
     assert_parity(dev, ora, iter_slack=0, aux=("p", "sd", "w"))
 
 
+@pytest.mark.parametrize("nx,ny,cap", [(64, 48, 73), (131, 77, 100), (200, 120, 1000), (3, 3, 60), (1024, 640, 400)])
+def test_jacobi_matches_oracle(nx, ny, cap):
+    """Jacobi: per-function kernels bit-exact, fused solve element-wise
+    bit-exact too (the sweep has no data-dependent control flow before the iteration cap)."""
+    s = lambda: classic_settings(nx, ny=ny, steps=1, solver="jacobi", maxiters=cap)
+    # per-function path, kernel by kernel
+    d, _ = tl.initialiseapp(s(), backend=_device())
+    o, _ = tl.initialiseapp(s(), backend=_oracle())
+    st = s()
+    rx, ry = st.dtinit / st.dx ** 2, st.dtinit / st.dy ** 2
+    for c in (d, o):
+        tl.haloupdate(c, st, 1, ["energy", "density"])
+        c.jacobi_init(st.coefficient, rx, ry)
+    for f in ("u", "u0", "kx", "ky"):
+        np.testing.assert_array_equal(d.get_field(f), o.get_field(f), err_msg=f)
+    for _ in range(3):
+        ed, eo = d.jacobi_iterate(), o.jacobi_iterate()
+        assert abs(ed - eo) <= SUM_TOL * abs(eo)
+        d.haloupdate(["u"], 1); o.haloupdate(["u"], 1)
+        np.testing.assert_array_equal(d.get_field("u"), o.get_field("u"))
+        np.testing.assert_array_equal(d.get_field("r"), o.get_field("r"))
+    d.close(); o.close()
+    # whole solves: fused device path vs oracle, and the stepwise host loop on the device
+    dev, ora = run(_device(), s()), run(_oracle(), s())
+    assert dev[1][0]["iters"] == ora[1][0]["iters"] <= cap     # converges on a 50th-iteration residual or hits the cap
+    assert abs(dev[1][0]["error"] - ora[1][0]["error"]) <= 1e-9 * abs(ora[1][0]["error"])
+    np.testing.assert_array_equal(dev[0].get_field("u"), ora[0].get_field("u"))
+    np.testing.assert_array_equal(dev[0].get_field("energy"), ora[0].get_field("energy"))
+    assert_parity(dev, ora, iter_slack=0)
+    step = run(_device(), s(), stepwise=True)
+    np.testing.assert_array_equal(step[0].get_field("u"), ora[0].get_field("u"))
+
+
+def test_jacobi_post_solve_r_and_coefficient_check():
+    for cap in (49, 50):     # r = previous iterate / r = the 50th-iteration residual
+        s = lambda: classic_settings(40, ny=56, steps=1, solver="jacobi", maxiters=cap, checkresult=False)
+        d, _ = tl.initialiseapp(s(), backend=_device())
+        o, _ = tl.initialiseapp(s(), backend=_oracle())
+        st = s()
+        rx, ry = st.dtinit / st.dx ** 2, st.dtinit / st.dy ** 2
+        for c in (d, o):
+            tl.haloupdate(c, st, 1, ["energy", "density"])
+        a, b = d.jacobi_solve(st, rx, ry), o.jacobi_solve(st, rx, ry)
+        assert a["iters"] == b["iters"] == cap
+        assert abs(a["error"] - b["error"]) <= SUM_TOL * abs(b["error"])
+        np.testing.assert_array_equal(d.get_field("u"), o.get_field("u"))
+        np.testing.assert_array_equal(d.get_field("r"), o.get_field("r"))
+        d.close(); o.close()
+    from tealeaf_jl_b200 import lib
+    d, _ = tl.initialiseapp(classic_settings(16, steps=1), backend=_device())
+    with pytest.raises(lib.TeaLeafError):
+        d.jacobi_init(0, 1.0, 1.0)          # Jacobi.jl:34-36
+    d.close()
+
+
 def test_errorswitch_and_maxiters_paths():
     for solver in ("cheby", "ppcg"):
         s = lambda: classic_settings(96, steps=1, solver=solver, errorswitch=True, epslim=1e-3)

@@ -160,3 +160,50 @@ def test_golden_values():
         assert [r["iters"] for r in recs] == case["iters"], case
         for k in ("vol", "mass", "ie", "temp"):
             assert abs(final[k] - case["final"][k]) <= 1e-13 * abs(case["final"][k]), (case, k)
+
+
+def test_jacobi_oracle_matches_numpy_twin_and_converges_towards_cg():
+    """Jacobi: the C oracle and the NumPy twin take
+    the same iterations element for element, the every-50th-iteration true residual replaces the
+    error, and the (slow) iteration approaches the CG solution of the same system."""
+    s = classic_settings(48, ny=40, steps=1, solver="jacobi", maxiters=73)
+    chunk, geom = tl.initialiseapp(s, backend=OracleChunk)
+    tl.haloupdate(chunk, s, 1, ["energy", "density"])
+    tw = Twin(chunk.get_field("density"), chunk.get_field("energy"), s.halodepth, s.coefficient)
+    rx, ry = s.dtinit / s.dx ** 2, s.dtinit / s.dy ** 2
+    got = chunk.jacobi_solve(s, rx, ry)
+    want = tw.jacobi_solve(rx, ry, s.eps, s.maxiters)
+    assert got["iters"] == want["iters"] == 73
+    np.testing.assert_array_equal(chunk.get_field("kx"), tw.kx)
+    np.testing.assert_array_equal(chunk.get_field("ky"), tw.ky)
+    np.testing.assert_array_equal(chunk.get_field("u"), tw.u)       # element-wise: bit-identical
+    np.testing.assert_array_equal(chunk.get_field("r"), tw.r)       # r = the previous iterate (Jacobi.jl:64)
+    assert abs(got["error"] / want["error"] - 1) < 1e-12
+    # at a multiple of 50 the error is the squared true residual and r holds the residual
+    # (the classic deck is strongly diagonally dominant: the test sum(r.r) < eps fires at tt = 100)
+    s2 = classic_settings(48, ny=40, steps=1, solver="jacobi", maxiters=230)
+    c2, _ = tl.initialiseapp(s2, backend=OracleChunk)
+    tl.haloupdate(c2, s2, 1, ["energy", "density"])
+    g2 = c2.jacobi_solve(s2, rx, ry)
+    assert g2["iters"] == 100 and tw.__class__(c2.get_field("density"), c2.get_field("energy"), s2.halodepth,
+                                               s2.coefficient).jacobi_solve(rx, ry, s2.eps, 230)["iters"] == 100
+    assert abs(g2["error"] - c2.norm2("r")) <= 1e-12 * g2["error"] and g2["error"] < s2.eps
+    # stepwise host loop == the oracle's own driver
+    s3 = classic_settings(48, ny=40, steps=1, solver="jacobi", maxiters=230)
+    c3, _ = tl.initialiseapp(s3, backend=OracleChunk)
+    tl.haloupdate(c3, s3, 1, ["energy", "density"])
+    g3 = tl.get_solver("jacobi").solve_stepwise(c3, s3, rx, ry)
+    assert g3["iters"] == 100 and g3["error"] == g2["error"]
+    np.testing.assert_array_equal(c3.get_field("u"), c2.get_field("u"))
+    # Jacobi and CG solve the same system: after many sweeps the iterate is close to CG's answer
+    s4 = classic_settings(24, ny=24, steps=1, solver="jacobi", maxiters=600)
+    c4, _ = tl.initialiseapp(s4, backend=OracleChunk)
+    tl.haloupdate(c4, s4, 1, ["energy", "density"])
+    c4.jacobi_solve(s4, s4.dtinit / s4.dx ** 2, s4.dtinit / s4.dy ** 2)
+    s5 = classic_settings(24, ny=24, steps=1, solver="cg")
+    c5, _ = tl.initialiseapp(s5, backend=OracleChunk)
+    tl.haloupdate(c5, s5, 1, ["energy", "density"])
+    c5.cg_solve(s5, s5.dtinit / s5.dx ** 2, s5.dtinit / s5.dy ** 2)
+    a, b = interior(c4.get_field("u")), interior(c5.get_field("u"))
+    assert np.abs(a - b).max() / np.abs(b).max() < 1e-12
+
