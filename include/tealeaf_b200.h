@@ -96,6 +96,22 @@ int tl_get_field(tl_ctx *ctx, int field, double *host, long ld);
 /* `chunk.dst .= chunk.src` on the whole array, device to device (src/TeaLeaf.jl:41) */
 int tl_copy_field(tl_ctx *ctx, int dst_field, int src_field);
 
+/* One `state` line of tea.in, src/settings.jl:20-29 (bounds already nudged by +-dx/100, :159-162). */
+#define TL_GEOM_RECTANGULAR 0
+#define TL_GEOM_CIRCULAR 1
+#define TL_GEOM_POINT 2
+typedef struct tl_state {
+  double density, energy, xmin, ymin, xmax, ymax, radius;
+  int geometry;   /* TL_GEOM_* */
+  int reserved;
+} tl_state;
+/* setchunkstate!, src/chunk.jl:122-151, on the device: paints density, energy0 and u of this
+ * tile (halo cells included) from the state list; vertex coordinates as Chunk(settings) builds
+ * them (src/chunk.jl:76-77): vertexx[k] = xmin + dx*(k - 1 - halo_depth + x0), 1-based k, where
+ * (x0, y0) is the tile's offset in the global mesh (0, 0 for a single chunk). */
+int tl_paint_states(tl_ctx *ctx, int nstates, const tl_state *states, double xmin, double ymin,
+                    double dx, double dy, int x0, int y0);
+
 /* ---- kernels, one per reference function -------------------------------------- */
 /* haloupdate!/updateface!, src/kernels.jl:146-159, :191-210 (depth-`depth` faces of every
  * field in field_mask; the sticky `toexchange` set stays on the Julia side). */

@@ -219,27 +219,39 @@ end
 TeaLeaf.CG.p!(chunk::B200Chunk, hd::Int, β::Float64) =
     check(chunk, ccall((:tl_cg_calc_p, LIB), Cint, (Ptr{Cvoid}, Cdouble), chunk.ctx, β))
 
+# ---- setchunkstate! (src/chunk.jl:122-151) on the device -------------------------------------------
+struct CState   # tl_state in include/tealeaf_b200.h
+    density::Cdouble; energy::Cdouble; xmin::Cdouble; ymin::Cdouble; xmax::Cdouble; ymax::Cdouble
+    radius::Cdouble; geometry::Cint; reserved::Cint
+end
+const GEOM_ID = Dict(TeaLeaf.Rectangular => 0, TeaLeaf.Circular => 1, TeaLeaf.Point => 2)
+function TeaLeaf.setchunkstate!(chunk::B200Chunk, set::Settings; x0::Int = 0, y0::Int = 0)
+    cs = [CState(s.density, s.energy, s.xmin, s.ymin, s.xmax, s.ymax, s.radius, GEOM_ID[s.geometry], 0)
+          for s in set.states]
+    check(chunk, ccall((:tl_paint_states, LIB), Cint,
+                       (Ptr{Cvoid}, Cint, Ptr{CState}, Cdouble, Cdouble, Cdouble, Cdouble, Cint, Cint),
+                       chunk.ctx, length(cs), cs, set.xmin, set.ymin, set.dx, set.dy, x0, y0))
+end
+
 # ---- application entry (src/TeaLeaf.jl:35-44) -----------------------------------------------------
 """
     initialiseapp!(settings; device = 0) -> B200Chunk
 
-`initialiseapp!` with the device chunk: the reference's own `Chunk`/`setchunkstate!` paint the
-state on the host, the painted `density`/`energy0`/`u` are uploaded once, and the rest of
-`initialiseapp!` (halo priming, `energy .= energy0`) runs on the device.
+`initialiseapp!` with the device chunk: `setchunkstate!` paints `density`/`energy0`/`u` on the
+device from `settings.states` (`tl_paint_states`, bit-identical to the host painter), and the rest
+of `initialiseapp!` (halo priming, `energy .= energy0`) runs on the device as well.  (A host that
+prefers the reference's own painter calls `upload!` with `host.density`, `host.energy0`, `host.u`.)
 """
 function initialiseapp!(settings::Settings; device::Int = 0)::B200Chunk
-    host = Chunk(settings)
-    setchunkstate!(host, settings.states)
     chunk = B200Chunk(settings; device = device)
-    upload!(chunk, :density, host.density)
-    upload!(chunk, :energy0, host.energy0)
-    upload!(chunk, :u, host.u)
+    setchunkstate!(chunk, settings)
     TeaLeaf.Kernels.haloupdate!(chunk, settings, 1, [:density, :energy0, :energy])
     check(chunk, ccall((:tl_copy_field, LIB), Cint, (Ptr{Cvoid}, Cint, Cint), chunk.ctx, FIELD_ID[:energy], FIELD_ID[:energy0]))
     # route `set.solver.solve!` to the device modules
     settings.solver = settings.solver === TeaLeaf.CG ? CG :
                       settings.solver === TeaLeaf.Cheby ? Cheby :
-                      settings.solver === TeaLeaf.PPCG ? PPCG : throw("solver not available on the B200 path")
+                      settings.solver === TeaLeaf.PPCG ? PPCG :
+                      settings.solver === TeaLeaf.Jacobi ? Jacobi : throw("solver not available on the B200 path")
     return chunk
 end
 

@@ -16,13 +16,19 @@ from .solvers import get_solver, haloupdate
 log = logging.getLogger("tealeaf")
 
 
-def upload_initial_state(chunk, settings: Settings, geom: HostGeometry | None = None):
-    """The field part of `initialiseapp!` (src/TeaLeaf.jl:35-44) for an existing backend chunk."""
+def upload_initial_state(chunk, settings: Settings, geom: HostGeometry | None = None, host_paint: bool = False):
+    """The field part of `initialiseapp!` (src/TeaLeaf.jl:35-44) for an existing backend chunk.
+    A backend that can paint the states itself (DeviceChunk: `tl_paint_states`, bit-identical to
+    the host painter -- tests/test_gpu_parity.py) does so; otherwise (the oracle, or
+    host_paint=True) the host paints and the three fields are uploaded."""
     geom = geom or HostGeometry(settings)
-    density, energy0, u = paint_states(settings, geom)          # setchunkstate!, TeaLeaf.jl:37
-    chunk.set_field("density", density)
-    chunk.set_field("energy0", energy0)
-    chunk.set_field("u", u)
+    if hasattr(chunk, "paint_states") and not host_paint:
+        chunk.paint_states(settings, geom)                          # setchunkstate!, TeaLeaf.jl:37
+    else:
+        density, energy0, u = paint_states(settings, geom)
+        chunk.set_field("density", density)
+        chunk.set_field("energy0", energy0)
+        chunk.set_field("u", u)
     haloupdate(chunk, settings, 1, ["density", "energy0", "energy"])  # TeaLeaf.jl:39
     chunk.copy_field("energy", "energy0")                       # TeaLeaf.jl:41
     return geom

@@ -524,6 +524,30 @@ extern "C" int tl_copy_field(tl_ctx *c, int dst_field, int src_field) {
   return TL_OK;
 }
 
+// setchunkstate! on the device (src/chunk.jl:122-151)
+extern "C" int tl_paint_states(tl_ctx *c, int nstates, const tl_state *states, double xmin, double ymin, double dx,
+                               double dy, int x0, int y0) {
+  if (!c || !states || nstates < 1) return tl_fail(c, TL_ERR_ARG, "tl_paint_states: bad argument");
+  if (nstates > TL_MAX_STATES) return tl_fail(c, TL_ERR_ARG, "tl_paint_states: more than %d states", TL_MAX_STATES);
+  CU(c, cudaSetDevice(c->device));
+  PaintParams P;
+  memset(&P, 0, sizeof P);
+  P.n = nstates; P.xmin = xmin; P.ymin = ymin; P.dx = dx; P.dy = dy; P.x0 = x0; P.y0 = y0;
+  for (int q = 0; q < nstates; q++) {
+    if (states[q].geometry < TL_GEOM_RECTANGULAR || states[q].geometry > TL_GEOM_POINT)
+      return tl_fail(c, TL_ERR_ARG, "tl_paint_states: state %d has an unknown geometry", q + 1);
+    P.s[q].density = states[q].density; P.s[q].energy = states[q].energy;
+    P.s[q].xmin = states[q].xmin; P.s[q].ymin = states[q].ymin; P.s[q].xmax = states[q].xmax; P.s[q].ymax = states[q].ymax;
+    P.s[q].radius = states[q].radius; P.s[q].geometry = states[q].geometry;
+  }
+  c->u_cur = 0;
+  k_paint_states<<<c->basic_grid, TL_BASIC_THREADS, 0, c->stream>>>(c->g, P, c->buf[TL_DENSITY], c->buf[TL_ENERGY0], c->buf[TL_U]);
+  c->launches++;
+  CHECK_LAUNCH(c);
+  CU(c, cudaStreamSynchronize(c->stream));
+  return TL_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // per-function kernels
 // ---------------------------------------------------------------------------------------

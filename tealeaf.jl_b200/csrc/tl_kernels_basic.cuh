@@ -187,6 +187,40 @@ __global__ void k_ppcg_inner2(Geo g, double alpha, double beta, const double *__
   }
 }
 
+// setchunkstate!, chunk.jl:122-151 ([k,j] indexing: Appendix A #3; celly from vertexy: A #4).
+// Every state in turn, the first included, later states overwrite earlier ones; then
+// u = energy0 * density on all but the outer ring (halo(ch, 1), chunk.jl:149-150).
+#define TL_MAX_STATES 32
+struct PaintState { double density, energy, xmin, ymin, xmax, ymax, radius; int geometry, pad; };
+struct PaintParams {
+  int n;
+  double xmin, ymin, dx, dy;
+  int x0, y0;
+  PaintState s[TL_MAX_STATES];
+};
+__global__ void k_paint_states(Geo g, const PaintParams P, double *density, double *energy0, double *u) {
+  TL_RECT_LOOP(-g.hd, g.nx + g.hd, -g.hd, g.ny + g.hd) {
+    // chunk.jl:76-77: vertex k (0-based over the padded array) = min + d * (k - hd + offset)
+    const double vx0 = P.xmin + P.dx * (double)(i + P.x0), vx1 = P.xmin + P.dx * (double)(i + 1 + P.x0);
+    const double vy0 = P.ymin + P.dy * (double)(j + P.y0), vy1 = P.ymin + P.dy * (double)(j + 1 + P.y0);
+    const double cx = 0.5 * (vx0 + vx1), cy = 0.5 * (vy0 + vy1);
+    double d = P.s[0].density, e = P.s[0].energy;
+    for (int q = 0; q < P.n; q++) {
+      const PaintState &s = P.s[q];
+      bool apply;
+      if (s.geometry == 0) apply = vx1 >= s.xmin && vx0 < s.xmax && vy1 >= s.ymin && vy0 < s.ymax;
+      else if (s.geometry == 1) apply = (cx - s.xmin) * (cx - s.xmin) + (cy - s.ymin) * (cy - s.ymin) <= s.radius * s.radius;
+      else apply = vx0 == s.xmin && vy0 == s.ymin;
+      if (apply) { d = s.density; e = s.energy; }
+    }
+    const long o = (long)j * g.pitch + i;
+    density[o] = d;
+    energy0[o] = e;
+    const bool ring = i == -g.hd || i == g.nx + g.hd - 1 || j == -g.hd || j == g.ny + g.hd - 1;
+    u[o] = ring ? 0.0 : e * d;
+  }
+}
+
 // ---- Jacobi (src/solvers/Jacobi.jl) ----------------------------
 // Jacobi.jl:39-41: u0 = u = energy .* density on the whole array
 __global__ void k_jacobi_init_fields(Geo g, const double *__restrict__ energy, const double *__restrict__ density,

@@ -90,6 +90,17 @@ class DeviceChunk:
     def get_field_raw(self, name: str, ptr: int, ld: int):
         self._ck(self._l.tl_get_field(self.ctx, FIELD_IDS[name], C.c_void_p(ptr), ld))
 
+    def paint_states(self, settings: Settings, geom) -> None:
+        """`setchunkstate!` (src/chunk.jl:122-151) on the device: density, energy0, u."""
+        from .settings import CIRCULAR, POINT, RECTANGULAR
+        gid = {RECTANGULAR: 0, CIRCULAR: 1, POINT: 2}
+        arr = (_lib.PaintState * len(settings.states))()
+        for q, st in enumerate(settings.states):
+            arr[q] = _lib.PaintState(st.density, st.energy, st.xmin, st.ymin, st.xmax, st.ymax, st.radius,
+                                     gid[st.geometry], 0)
+        self._ck(self._l.tl_paint_states(self.ctx, len(settings.states), arr, settings.xmin, settings.ymin,
+                                         settings.dx, settings.dy, geom.x0, geom.y0))
+
     def copy_field(self, dst: str, src: str):
         self._ck(self._l.tl_copy_field(self.ctx, FIELD_IDS[dst], FIELD_IDS[src]))
 

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libtealeaf_b200.so")
+# TEALEAF_B200_LIB overrides the in-tree build (A/B runs of two builds, packaged installs)
+LIB_PATH = os.environ.get("TEALEAF_B200_LIB") or os.path.join(HERE, "csrc", "libtealeaf_b200.so")
 
 TL_OK = 0
 TL_ERR_ARG, TL_ERR_CUDA, TL_ERR_NO_DEVICE, TL_ERR_EIGEN, TL_ERR_COMM, TL_ERR_STATE = -1, -2, -3, -4, -5, -6
@@ -39,6 +40,12 @@ _D = C.c_double
 _I = C.c_int
 _DP = C.POINTER(C.c_double)
 
+class PaintState(C.Structure):
+    """tl_state in include/tealeaf_b200.h"""
+    _fields_ = [("density", _D), ("energy", _D), ("xmin", _D), ("ymin", _D), ("xmax", _D), ("ymax", _D),
+                ("radius", _D), ("geometry", _I), ("reserved", _I)]
+
+
 # name -> (restype, argtypes); every symbol include/tealeaf_b200.h declares
 SIGNATURES = {
     "tl_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I]),
@@ -54,6 +61,7 @@ SIGNATURES = {
     "tl_set_field": (_I, [_P, _I, _P, C.c_long]),
     "tl_get_field": (_I, [_P, _I, _P, C.c_long]),
     "tl_copy_field": (_I, [_P, _I, _I]),
+    "tl_paint_states": (_I, [_P, _I, C.POINTER(PaintState), _D, _D, _D, _D, _I, _I]),
     "tl_halo_update": (_I, [_P, C.c_uint, _I]),
     "tl_cg_init": (_I, [_P, _I, _D, _D, _DP]),
     "tl_cg_calc_w": (_I, [_P, _DP]),

@@ -150,6 +150,50 @@ def test_errors_are_reported_not_thrown():
     c.close()
 
 
+MIXED_DECK = """*tea
+state 1 density=100.0 energy=0.0001
+state 2 density=0.1 energy=25.0 geometry=rectangle xmin=0.0 xmax=1.0 ymin=1.0 ymax=2.0
+state 3 density=5.0 energy=2.5 geometry=circular xmin=6.0 ymin=4.0 radius=2.25
+state 4 density=0.3 energy=7.0 geometry=point xmin=2.5 ymin=7.5
+state 5 density=0.1 energy=0.1 geometry=rectangle xmin=5.0 xmax=10.0 ymin=7.0 ymax=8.0
+x_cells={nx}
+y_cells={ny}
+xmin=0.0
+ymin=0.0
+xmax=10.0
+ymax=10.0
+initial_timestep=0.004
+end_step=1
+use_cg
+*endtea
+"""
+
+
+@pytest.mark.parametrize("nx,ny,tile", [(40, 40, None), (97, 61, None), (80, 64, (40, 32, 40, 32)), (80, 64, (0, 32, 27, 32))])
+def test_device_painter_is_bit_identical_to_the_host_painter(nx, ny, tile):
+    """tl_paint_states (setchunkstate!, src/chunk.jl:122-151 on the device) vs the host mirror:
+    rectangle, circular and point states, whole mesh and tiles with an offset."""
+    from tealeaf_jl_b200.chunk import HostGeometry, paint_states
+    for deck in (None, MIXED_DECK):
+        s = classic_settings(nx, ny=ny, steps=1) if deck is None else tl.parse_settings_text(deck.format(nx=nx, ny=ny))
+        geom = HostGeometry(s, tile=tile)
+        d = _device()(geom.nx, geom.ny, s.halodepth, 100)
+        d.paint_states(s, geom)
+        density, energy0, u = paint_states(s, geom)
+        np.testing.assert_array_equal(d.get_field("density"), density)
+        np.testing.assert_array_equal(d.get_field("energy0"), energy0)
+        np.testing.assert_array_equal(d.get_field("u"), u)
+        d.close()
+    # and the whole initialiseapp! agrees whichever side paints
+    s = classic_settings(64, ny=48, steps=1)
+    a, _ = tl.initialiseapp(s, backend=_device())
+    b = _device()(64, 48, s.halodepth, s.maxiters)
+    tl.upload_initial_state(b, s, host_paint=True)
+    for f in ("density", "energy0", "energy", "u"):
+        np.testing.assert_array_equal(a.get_field(f), b.get_field(f), err_msg=f)
+    a.close(); b.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # whole solves
 # ---------------------------------------------------------------------------------------------
