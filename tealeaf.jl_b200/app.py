@@ -60,13 +60,76 @@ def fieldsummary(chunk, settings: Settings, geom: HostGeometry):
     return out
 
 
+def julia_float(v: float) -> str:
+    """`string(::Float64)` as Julia prints it (shortest round-trip digits; fixed notation for
+    decimal exponents -5 < e < 6, else `d.ddde±x`), so that debug dumps diff against the reference's."""
+    if v != v:
+        return "NaN"
+    if v in (float("inf"), float("-inf")):
+        return "Inf" if v > 0 else "-Inf"
+    if v == 0.0:
+        return "-0.0" if str(v).startswith("-") else "0.0"
+    mant, _, exp = f"{v!r}".partition("e")
+    sign = "-" if mant.startswith("-") else ""
+    mant = mant.lstrip("-")
+    ip, _, fp = mant.partition(".")
+    digits = (ip + fp).lstrip("0") or "0"
+    e10 = (int(exp) if exp else 0) + len(ip.lstrip("0")) - 1 if ip.strip("0") else \
+        (int(exp) if exp else 0) - (len(fp) - len(fp.lstrip("0"))) - 1
+    digits = digits.rstrip("0") or "0"
+    if -5 < e10 < 6:
+        if e10 >= 0:
+            whole, frac = digits[:e10 + 1].ljust(e10 + 1, "0"), digits[e10 + 1:]
+            return f"{sign}{whole}.{frac or '0'}"
+        return f"{sign}0.{'0' * (-e10 - 1)}{digits}"
+    return f"{sign}{digits[0]}.{digits[1:] or '0'}e{e10}"
+
+
+def debugrecord(settings: Settings, chunk, geom: HostGeometry):
+    """`debugrecord`, src/TeaLeaf.jl:90-103: appends every `Chunk` attribute (src/chunk.jl:19-60, in
+    declaration order, one matrix column per line) to `settings.debugfile`.  Device fields are
+    downloaded with `get_field`; `density0`, `mi` (never written on the path) are zeros; `xarea`/
+    `yarea` are skipped (Appendix A #5: never filled consistently, never read)."""
+    if not settings.debugfile:
+        return
+    import numpy as np
+    log.info("Writing debug data to %s", settings.debugfile)
+    zeros = np.zeros((geom.x, geom.y))
+
+    def mat(a):
+        return "\n".join(" ".join(julia_float(float(v)) for v in a[:, j]) for j in range(a.shape[1]))
+
+    def vec(a):
+        return " ".join(julia_float(float(v)) for v in a)
+
+    n = getattr(chunk, "maxiters", 0)
+    pick = lambda name: vec(np.asarray(getattr(chunk, name, np.zeros(n)))[:n])
+    items = [("density0", mat(zeros)), ("density", mat(chunk.get_field("density"))),
+             ("energy0", mat(chunk.get_field("energy0"))), ("energy", mat(chunk.get_field("energy")))]
+    items += [(f, mat(chunk.get_field(f))) for f in ("u", "u0", "p", "r")]
+    items += [("mi", mat(zeros))] + [(f, mat(chunk.get_field(f))) for f in ("w", "kx", "ky", "sd")]
+    items += [("vertexx", vec(geom.vertexx)), ("vertexy", vec(geom.vertexy)), ("cellx", vec(geom.cellx)),
+              ("celly", vec(geom.celly)), ("volume", mat(zeros + geom.cell_volume))]
+    items += [("θ", julia_float(getattr(chunk, "theta", 0.0))), ("eigmin", julia_float(getattr(chunk, "eigmin", 0.0))),
+              ("eigmax", julia_float(getattr(chunk, "eigmax", 0.0)))]
+    items += [("cgα", pick("cgalpha")), ("cgβ", pick("cgbeta")), ("chebyα", pick("chalpha")), ("chebyβ", pick("chbeta"))]
+    with open(settings.debugfile, "a", encoding="utf-8") as fh:
+        for name, text in items:
+            fh.write(f"{name}\n{text}\n\n")
+        fh.write("\n\n")
+
+
 def diffuse(chunk, settings: Settings, geom: HostGeometry, stepwise: bool = False, on_step=None):
     """`diffuse!`, src/TeaLeaf.jl:62-83.  Returns the per-step records."""
     if settings.endstep >= 2**62:
         raise ValueError("end_step is required (SURVEY Appendix A #22)")
     solver = get_solver(settings.solver)
     records = []
+    import os
+    if settings.debugfile and os.path.isfile(settings.debugfile):   # TeaLeaf.jl:63-65
+        os.remove(settings.debugfile)
     for tt in range(1, settings.endstep + 1):
+        debugrecord(settings, chunk, geom)                          # TeaLeaf.jl:68
         rx = settings.dtinit / settings.dx ** 2    # TeaLeaf.jl:69
         ry = settings.dtinit / settings.dy ** 2    # TeaLeaf.jl:70
         haloupdate(chunk, settings, 1, ["energy", "density"])   # TeaLeaf.jl:71

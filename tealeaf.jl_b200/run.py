@@ -19,7 +19,7 @@ def main(argv=None):
     ap.add_argument("-x", type=int, help="Number of x cells")              # run.jl:10-12
     ap.add_argument("-y", type=int, help="Number of y cells")              # run.jl:13-15
     ap.add_argument("-i", "--in-file", default="tea.in", help="Settings input file")   # run.jl:16-19
-    ap.add_argument("-O", "--debug-out", help="File to print debug state to (not supported on the device path)")
+    ap.add_argument("-O", "--debug-out", help="File to print debug state to")  # run.jl:20-22
     ap.add_argument("--stepwise", action="store_true", help="drive the solve kernel by kernel (per-function ABI)")
     ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args(argv)
@@ -31,6 +31,8 @@ def main(argv=None):
         settings.xcells = args.x
     if args.y:
         settings.ycells = args.y
+    if args.debug_out:
+        settings.debugfile = args.debug_out                                # run.jl:41-43
     settings.recompute_spacing()                                           # Appendix A #23
     chunk, geom = initialiseapp(settings, device=args.device)              # run.jl:45
     records, final = diffuse(chunk, settings, geom, stepwise=args.stepwise)  # run.jl:47

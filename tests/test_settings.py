@@ -105,3 +105,34 @@ def test_reflect_halo_host():
     assert (b[1, 2:-2] == a[2, 2:-2]).all() and (b[0, 2:-2] == a[3, 2:-2]).all()
     assert (b[-2, 2:-2] == a[-3, 2:-2]).all() and (b[2:-2, 0] == a[2:-2, 3]).all()
     assert b[0, 0] == a[0, 0]   # corners untouched, like the reference
+
+
+def test_debugrecord_dump_follows_the_reference_format(tmp_path):
+    """`--debug-out` (run.jl:20-22, TeaLeaf.jl:63-68, :90-107): one block per Chunk attribute in
+    declaration order, matrices one column (fixed jj) per line, Julia float formatting; the file is
+    restarted by diffuse! and appended to at every timestep.  Runs on the CPU oracle backend here;
+    the device backend goes through the same code with tl_get_field."""
+    import tealeaf_jl_b200 as tl
+    from tealeaf_jl_b200.app import julia_float
+    from oracle.oracle import OracleChunk
+    from conftest import classic_settings
+    assert [julia_float(v) for v in (100.0, 1e-4, 1e-5, 0.1, 1e6, -2.5e10, 0.0)] == \
+        ["100.0", "0.0001", "1.0e-5", "0.1", "1.0e6", "-2.5e10", "0.0"]
+    out = tmp_path / "debug.txt"
+    out.write_text("stale")
+    s = classic_settings(6, ny=5, steps=2, solver="cg")
+    s.debugfile = str(out)
+    chunk, geom = tl.initialiseapp(s, backend=OracleChunk)
+    tl.diffuse(chunk, s, geom)
+    text = out.read_text(encoding="utf-8")
+    assert "stale" not in text
+    blocks = text.split("\n\n\n\n")
+    assert len([b for b in blocks if b.strip()]) == 2            # one record per timestep
+    names = [blk.split("\n")[0] for blk in blocks[0].split("\n\n") if blk.strip()]
+    assert names == ["density0", "density", "energy0", "energy", "u", "u0", "p", "r", "mi", "w", "kx", "ky", "sd",
+                     "vertexx", "vertexy", "cellx", "celly", "volume", "θ", "eigmin", "eigmax", "cgα", "cgβ",
+                     "chebyα", "chebyβ"]
+    dens = [blk for blk in blocks[0].split("\n\n") if blk.startswith("density\n")][0].split("\n")[1:]
+    assert len(dens) == 5 + 4 and all(len(row.split(" ")) == 6 + 4 for row in dens)
+    assert {v for row in dens for v in row.split(" ")} == {"100.0", "0.1"}
+
