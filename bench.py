@@ -187,6 +187,8 @@ def run_b200(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
     torch.cuda.set_device(local_rank)
+    from tealeaf_jl_b200.dist import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank)      # before any pinned allocation (first touch)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -358,7 +360,8 @@ def run_b200(args):
             "solve_only_ms_per_step": solve_ms / args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * field_bytes,
-                    "d2h_bytes_per_step": field_bytes + 32, "ms_per_step": 1e3 * e2e_wall / args.steps},
+                    "d2h_bytes_per_step": field_bytes + 32, "ms_per_step": 1e3 * e2e_wall / args.steps,
+                    "host_numa_binding": numa},
             "gpu_launches": int(launches), "clocks": clocks,
             **({"same_tile_single_gpu": {"value": solo, "unit": UNIT, "note":
                 "this rank's tile solved alone (1x1, 60 CG iterations incl. init) in the same job; "
@@ -379,6 +382,8 @@ def main():
     ap.add_argument("--cap-iters", type=int, default=200, help="N>1: CG iterations per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import __graft_entry__
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         __graft_entry__.build()

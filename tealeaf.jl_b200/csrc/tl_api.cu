@@ -101,6 +101,8 @@ struct tl_ctx {
   CommBlob peer_blob[4]{};
   void *rank_slab[TL_MAX_RANKS]{};   // every other tile's slab, CUDA-IPC mapped (mailboxes; the neighbours' fields)
   bool comm_ready = false;
+  int use_pdl = 0;          // programmatic dependent launch between the kernels of the iteration loops: measured
+                            // SLOWER (profiles/r01d_pdl_sweep.log: 1024^2 CG 24.7 -> 27.6 us/iteration), kept as an option
   int comm_fused = 1;       // 1: halo pushes + mailbox allreduce inside the kernels; 0: halo-pull kernels + NCCL
   CommDev *d_comm = nullptr;   // device copy of the mailbox table (in the slab)
   MailSlot *mail = nullptr;
@@ -122,6 +124,30 @@ static int tl_fail(tl_ctx *c, int code, const char *fmt, ...) {
                                              cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 #define CHECK_LAUNCH(c) CU(c, cudaGetLastError())
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+// Launch of a hot-loop kernel.  With use_pdl the launch carries the programmatic-stream-
+// serialization attribute (a programmatic edge when captured into a graph): the kernel may become
+// resident while its predecessor drains, and waits in tl_pdl_entry() (griddepcontrol.wait) until
+// the predecessor has completed and flushed -- the launch latency between the dependent kernels of
+// an iteration disappears from the critical path.
+template <typename P>
+static cudaError_t tl_launch(tl_ctx *c, void (*kern)(const P), int grid, int block, size_t smem, const P &params);
+
+template <typename P>
+static cudaError_t tl_launch(tl_ctx *c, void (*kern)(const P), int grid, int block, size_t smem, const P &params) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = c->use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, params);
+}
 
 static double *field_ptr(tl_ctx *c, int f) {
   if (f == TL_P) return c->buf[c->p_cur ? B_P1 : TL_P];
@@ -330,6 +356,7 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "hint_stream") c->hint_stream = std::min(std::max(0, (int)value), 2);
   else if (n == "b_reverse") c->b_reverse = value != 0.0;
   else if (n == "comm_fused") c->comm_fused = value != 0.0;
+  else if (n == "use_pdl") c->use_pdl = value != 0.0;
   else if (n == "l2_persist_mb") c->l2_persist_mb = value;
   else if (n == "l2_hit_scale") c->l2_hit_scale = value;
   else if (n == "l2_persist_field") c->l2_persist_field = std::min(std::max(0, (int)value), (int)B_COUNT - 1);
@@ -808,7 +835,7 @@ static int launch_ring(tl_ctx *c, const CgAParams &P) {
     CU(c, cudaFuncSetAttribute(k_cg_fused_w_ring<U, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  k_cg_fused_w_ring<U, S, MINB><<<c->fused_grid, TL_FUSED_THREADS, smem, c->stream>>>(P);
+  CU(c, tl_launch(c, k_cg_fused_w_ring<U, S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }
 template <bool U>
@@ -832,7 +859,7 @@ static int launch_cheby_ring(tl_ctx *c, const ChebyParams &P) {
     CU(c, cudaFuncSetAttribute(k_cheby_fused_ring<FIRST, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  k_cheby_fused_ring<FIRST, S, MINB><<<c->fused_grid, TL_FUSED_THREADS, smem, c->stream>>>(P);
+  CU(c, tl_launch(c, k_cheby_fused_ring<FIRST, S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }
 static ChebyParams cheby_params(tl_ctx *c);
@@ -856,7 +883,7 @@ static int launch_ppcg_inner_ring(tl_ctx *c, const PpcgInnerParams &P) {
     CU(c, cudaFuncSetAttribute(k_ppcg_inner_ring<S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  k_ppcg_inner_ring<S, MINB><<<c->fused_grid, TL_FUSED_THREADS, smem, c->stream>>>(P);
+  CU(c, tl_launch(c, k_ppcg_inner_ring<S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }
 static PpcgInnerParams ppcg_inner_params(tl_ctx *c);
@@ -885,8 +912,7 @@ static int enqueue_cg_iteration(tl_ctx *c) {
   }
   TRY(launch_cg_a<true>(c));
   if (legacy) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
-  k_cg_fused_r<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
-  CHECK_LAUNCH(c);
+  CU(c, tl_launch(c, k_cg_fused_r, c->pw_grid, TL_FUSED_THREADS, 0, cg_b_params(c)));
   if (legacy) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
   c->launches += 2;
   return TL_OK;
@@ -1172,8 +1198,7 @@ static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps) {
   }
   TRY(launch_cg_a<false>(c));
   if (legacy) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
-  k_ppcg_ur_sd<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(ppcg_ur_params(c));
-  CHECK_LAUNCH(c);
+  CU(c, tl_launch(c, k_ppcg_ur_sd, c->pw_grid, TL_FUSED_THREADS, 0, ppcg_ur_params(c)));
   for (int pp = 0; pp < inner_steps; pp++) {
     if (legacy) {
       TRY(tile_barrier(c));
@@ -1295,7 +1320,7 @@ static int launch_jacobi_ring(tl_ctx *c, const JacobiParams &P) {
     CU(c, cudaFuncSetAttribute(k_jacobi_fused_ring<S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  k_jacobi_fused_ring<S, MINB><<<c->fused_grid, TL_FUSED_THREADS, smem, c->stream>>>(P);
+  CU(c, tl_launch(c, k_jacobi_fused_ring<S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }
 static int launch_jacobi(tl_ctx *c) {
@@ -1311,8 +1336,7 @@ static int launch_jacobi(tl_ctx *c) {
   return TL_OK;
 }
 static int launch_jacobi_resid(tl_ctx *c, int force) {
-  k_jacobi_resid<<<c->basic_grid, TL_BASIC_THREADS, 0, c->stream>>>(jacobi_params(c, force));
-  CHECK_LAUNCH(c);
+  CU(c, tl_launch(c, k_jacobi_resid, c->basic_grid, TL_BASIC_THREADS, 0, jacobi_params(c, force)));
   c->launches++;
   return TL_OK;
 }
@@ -1380,7 +1404,7 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
   auto launch = [&]() -> int {
     if (k == "cg_fused_w") TRY(launch_cg_a<true>(c));
     else if (k == "cg_fused_w_nou") TRY(launch_cg_a<false>(c));
-    else if (k == "cg_fused_r") k_cg_fused_r<<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(cg_b_params(c));
+    else if (k == "cg_fused_r") CU(c, tl_launch(c, k_cg_fused_r, c->pw_grid, TL_FUSED_THREADS, 0, cg_b_params(c)));
     else if (k == "cheby_fused") TRY(launch_cheby<false>(c));
     else if (k == "ppcg_inner") TRY(launch_ppcg_inner(c));
     else return tl_fail(c, TL_ERR_ARG, "tl_time_kernel: unknown kernel %s", kernel);

@@ -103,6 +103,14 @@ __host__ __device__ inline bool tl_should_stop(int it, double rr, const StopCfg 
 
 #ifdef __CUDACC__
 
+// Programmatic dependent launch: let the next kernel of the stream become resident right away,
+// then wait until the previous one has completed and its writes are visible.  Both instructions
+// are no-ops for a kernel launched without the programmatic attribute.
+__device__ __forceinline__ void tl_pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ double tl_warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -116,6 +116,7 @@ struct CgBParams {
 };
 
 __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBParams P) {
+  tl_pdl_entry();
   __shared__ double sm[32];
   SolveState *st = P.st;
   const int it = st->iter;
@@ -264,6 +265,7 @@ struct PpcgUrParams {
 };
 
 __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_ppcg_ur_sd(const PpcgUrParams P) {
+  tl_pdl_entry();
   __shared__ double sm[32];
   SolveState *st = P.st;
   const int it = st->iter;

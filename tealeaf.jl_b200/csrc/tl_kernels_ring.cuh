@@ -44,6 +44,7 @@ __device__ __forceinline__ double tl_lds1(unsigned a) {
 // CG kernel A (algorithm and citations: CgAParams in tl_kernels_fused.cuh).
 template <bool UPDATE_U, int S, int MINB>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(const CgAParams P) {
+  tl_pdl_entry();
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
@@ -263,6 +264,7 @@ __device__ __forceinline__ void tl_stencil2(const Geo &g, const MarchCtx &m, boo
 // Chebyshev iteration (algorithm and citations: ChebyParams in tl_kernels_fused.cuh).
 template <bool FIRST, int S, int MINB>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(const ChebyParams P) {
+  tl_pdl_entry();
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
 // PPCG inner step (algorithm and citations: PpcgInnerParams in tl_kernels_fused.cuh).
 template <int S, int MINB>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(const PpcgInnerParams P) {
+  tl_pdl_entry();
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
@@ -446,6 +449,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(cons
 // Jacobi iteration (algorithm and citations: JacobiParams in tl_kernels_fused.cuh).
 template <int S, int MINB>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_jacobi_fused_ring(const JacobiParams P) {
+  tl_pdl_entry();
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
@@ -528,6 +532,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_jacobi_fused_ring(co
 // iteration kernel (whose tail exchange completed the halo pushes of u); idempotent, so the
 // launched-ahead copies after the stop rule fired leave the state unchanged.
 __global__ void __launch_bounds__(TL_BASIC_THREADS) k_jacobi_resid(const JacobiParams P) {
+  tl_pdl_entry();
   __shared__ double sm[32];
   SolveState *st = P.st;
   const int it = st->iter;

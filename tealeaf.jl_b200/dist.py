@@ -36,6 +36,42 @@ def grid_for(world: int):
     return px, world // px
 
 
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Pin this process (and hence its first-touch host allocations, pinned staging buffers
+    included) to the CPUs of the NUMA node the GPU hangs off, so that host<->device copies of
+    the 8 ranks of a box do not cross the socket interconnect.  Best effort: returns what it
+    did, never raises."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if visible:
+            tok = visible.split(",")[device_index].strip()
+            if tok.isdigit():
+                idx = int(tok)
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info = {"numa_node": node, "cpus": len(cpus)}
+    except Exception as exc:  # no NVML / sysfs layout differs: leave the affinity alone
+        info["error"] = str(exc)[:80]
+    return info
+
+
 def split(n: int, parts: int, idx: int):
     """(offset, size) of piece `idx` when n cells are cut into `parts` nearly equal pieces."""
     base, rem = divmod(n, parts)

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--inner", type=int, default=10)
     ap.add_argument("--comm", default="fused,nccl")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--opt", action="append", default=[], help="tl_set_option name=value (repeatable)")
     args = ap.parse_args()
 
     import torch
@@ -65,6 +66,9 @@ def main():
             chunk, geom, _ = tld.create_tile(s, dist, local_rank, options={"comm_fused": 1 if comm == "fused" else 0})
         else:
             chunk, geom = tl.initialiseapp(s, backend=DeviceChunk)
+        for kv in args.opt:
+            k, _, v = kv.partition("=")
+            chunk.set_option(k, float(v))
         rx, ry = s.dtinit / s.dx ** 2, s.dtinit / s.dy ** 2
         solver = get_solver(s.solver)
         best = None
@@ -90,7 +94,7 @@ def main():
         if rank == 0:
             print(json.dumps({
                 "solver": args.solver, "global_cells": [nx, ny], "n_gpus": world, "decomposition": f"{px}x{py}",
-                "comm": comm, "iters": best["iters"], "cg_iters": best["cg_iters"], "cheby_or_outer_iters": best["cheby_iters"],
+                "comm": comm, "options": args.opt, "iters": best["iters"], "cg_iters": best["cg_iters"], "cheby_or_outer_iters": best["cheby_iters"],
                 "inner_steps_total": best["inner_total"], "error": best["error"], "solve_ms": ms,
                 "cell_iterations_per_s": cells * work_iters / (ms * 1e-3),
                 "us_per_sweep": 1e3 * ms / max(work_iters, 1),
