@@ -293,6 +293,17 @@ def test_jacobi_post_solve_r_and_coefficient_check():
     d.close()
 
 
+@pytest.mark.parametrize("solver", ["cg", "cheby", "ppcg", "jacobi"])
+@pytest.mark.parametrize("hd,coef", [(3, 1), (4, 2)])
+def test_fused_solves_with_other_halo_depths_and_coefficient(solver, hd, coef):
+    """halo_depth != 2 changes the padded layout (pitch, row offsets) and the range kx/ky are set on;
+    coefficient = 2 is RECIP_CONDUCTIVITY (src/settings.jl:14)."""
+    s = lambda: classic_settings(90, ny=70, steps=1, solver=solver, halodepth=hd, coefficient=coef,
+                                 maxiters=400 if solver == "jacobi" else 10000)
+    dev, ora = run(_device(), s()), run(_oracle(), s())
+    assert_parity(dev, ora, iter_slack=1 if solver == "cg" else 0, fields=("u", "energy", "kx", "ky"))
+
+
 def test_errorswitch_and_maxiters_paths():
     for solver in ("cheby", "ppcg"):
         s = lambda: classic_settings(96, steps=1, solver=solver, errorswitch=True, epslim=1e-3)
