@@ -133,6 +133,18 @@ static int tl_fail(tl_ctx *c, int code, const char *fmt, ...) {
 template <typename P>
 static cudaError_t tl_launch(tl_ctx *c, void (*kern)(const P), int grid, int block, size_t smem, const P &params);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember which devices a
+// kernel instantiation has been prepared on (one static mask per instantiation).
+template <typename P>
+static int tl_prepare_smem(tl_ctx *c, void (*kern)(const P), int smem, unsigned long long *device_mask) {
+  const unsigned long long bit = 1ull << (c->device & 63);
+  if (!(*device_mask & bit)) {
+    CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    *device_mask |= bit;
+  }
+  return TL_OK;
+}
+
 template <typename P>
 static cudaError_t tl_launch(tl_ctx *c, void (*kern)(const P), int grid, int block, size_t smem, const P &params) {
   cudaLaunchConfig_t cfg;
@@ -830,11 +842,8 @@ static CgBParams cg_b_params(tl_ctx *c) {
 template <bool U, int S, int MINB>
 static int launch_ring(tl_ctx *c, const CgAParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(c, cudaFuncSetAttribute(k_cg_fused_w_ring<U, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_cg_fused_w_ring<U, S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_cg_fused_w_ring<U, S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }
@@ -854,11 +863,8 @@ static int launch_cg_a(tl_ctx *c) {
 template <bool FIRST, int S, int MINB>
 static int launch_cheby_ring(tl_ctx *c, const ChebyParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(c, cudaFuncSetAttribute(k_cheby_fused_ring<FIRST, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_cheby_fused_ring<FIRST, S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_cheby_fused_ring<FIRST, S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }
@@ -878,11 +884,8 @@ static int launch_cheby(tl_ctx *c) {
 template <int S, int MINB>
 static int launch_ppcg_inner_ring(tl_ctx *c, const PpcgInnerParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(c, cudaFuncSetAttribute(k_ppcg_inner_ring<S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_ppcg_inner_ring<S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_ppcg_inner_ring<S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }
@@ -1315,11 +1318,8 @@ static JacobiParams jacobi_params(tl_ctx *c, int force_resid) {
 template <int S, int MINB>
 static int launch_jacobi_ring(tl_ctx *c, const JacobiParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(c, cudaFuncSetAttribute(k_jacobi_fused_ring<S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_jacobi_fused_ring<S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_jacobi_fused_ring<S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }

@@ -64,3 +64,24 @@ def test_tiled_solvers_match_oracle(grid):
     r = _torchrun("mgpu_check.py", n, env=env)
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_two_devices_in_one_process():
+    """Two independent single-tile contexts on two GPUs of the same process (per-device kernel
+    attributes, per-context streams): both give the single-GPU result."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from tealeaf_jl_b200.device import DeviceChunk
+    outs = []
+    for dev in (1, 0, 1):
+        s = classic_settings(200, ny=130, steps=1, solver="ppcg")
+        chunk, geom = tl.initialiseapp(s, backend=DeviceChunk, device=dev)
+        recs, final = tl.diffuse(chunk, s, geom)
+        outs.append((recs[0]["iters"], final["temp"], chunk.get_field("u")))
+        chunk.close()
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and o[1] == outs[0][1]
+        np.testing.assert_array_equal(o[2], outs[0][2])
+
