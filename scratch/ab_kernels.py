@@ -9,6 +9,9 @@ for N in (4096, 8192):
     s = classic_settings(N, steps=1, solver='cg', maxiters=400)
     chunk, geom = tl.initialiseapp(s, backend=DeviceChunk)
     rx, ry = s.dtinit / s.dx ** 2, s.dtinit / s.dy ** 2
+    for kv in os.environ.get("TL_OPTS", "").split(","):
+        if kv:
+            chunk.set_option(kv.split("=")[0], float(kv.split("=")[1]))
     best = None
     for _ in range(3):
         chunk.copy_field("energy", "energy0")
