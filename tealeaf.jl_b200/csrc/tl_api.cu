@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <unistd.h>
 #ifdef TL_WITH_NCCL
 #include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
 #include <dlfcn.h>
@@ -65,6 +66,8 @@ struct CommBlob {  // what tl_comm_export hands to the other ranks
   long long buf_offset[B_COUNT];  // byte offset of interior cell (0,0) of each buffer in the slab
   long long mail_offset;          // byte offset of the tile's mailbox (tl_tile_exchange)
   int rank, device;
+  long long pid;                  // exporting process: tiles of the SAME process are wired by plain pointer
+  unsigned long long slab_ptr;    // (CUDA-IPC handles cannot be opened by the process that made them)
 };
 
 struct tl_ctx {
@@ -99,7 +102,9 @@ struct tl_ctx {
   int nbr_rank[4] = {-1, -1, -1, -1};
   void *peer_slab[4]{};
   CommBlob peer_blob[4]{};
+  CommBlob rank_blob[TL_MAX_RANKS]{};
   void *rank_slab[TL_MAX_RANKS]{};   // every other tile's slab, CUDA-IPC mapped (mailboxes; the neighbours' fields)
+  bool rank_ipc[TL_MAX_RANKS]{};     // true: mapped with cudaIpcOpenMemHandle (to be closed); false: same-process pointer
   bool comm_ready = false;
   int use_pdl = 0;          // programmatic dependent launch between the kernels of the iteration loops: measured
                             // SLOWER (profiles/r01d_pdl_sweep.log: 1024^2 CG 24.7 -> 27.6 us/iteration), kept as an option
@@ -340,7 +345,7 @@ extern "C" void tl_destroy(tl_ctx *c) {
   if (c->nccl && nccl_api().ok) nccl_api().CommDestroy(c->nccl);
 #endif
   for (int r = 0; r < TL_MAX_RANKS; r++)
-    if (c->rank_slab[r]) cudaIpcCloseMemHandle(c->rank_slab[r]);
+    if (c->rank_slab[r] && c->rank_ipc[r]) cudaIpcCloseMemHandle(c->rank_slab[r]);
   if (c->ev[0]) cudaEventDestroy(c->ev[0]);
   if (c->ev[1]) cudaEventDestroy(c->ev[1]);
   if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -399,6 +404,7 @@ extern "C" int tl_comm_export(tl_ctx *c, void *blob) {
   for (int i = 0; i < B_COUNT; i++) b.buf_offset[i] = (long long)((char *)c->buf[i] - c->slab);
   b.mail_offset = (long long)((char *)c->mail - c->slab);
   b.rank = c->rank; b.device = c->device;
+  b.pid = (long long)getpid(); b.slab_ptr = (unsigned long long)(uintptr_t)c->slab;
   memcpy(blob, &b, sizeof b);
   return TL_OK;
 }
@@ -419,38 +425,71 @@ extern "C" int tl_comm_unique_id(void *id128) {
 extern "C" int tl_comm_connect(tl_ctx *c, const void *all_blobs, const void *id128) {
   if (!c) return TL_ERR_ARG;
   if (c->nranks == 1) { c->comm_ready = true; return TL_OK; }
-  if (!all_blobs || !id128) return tl_fail(c, TL_ERR_ARG, "tl_comm_connect: blobs and NCCL id are required");
+  if (!all_blobs) return tl_fail(c, TL_ERR_ARG, "tl_comm_connect: the tiles' blobs are required");
   CU(c, cudaSetDevice(c->device));
   const CommBlob *blobs = (const CommBlob *)all_blobs;
   // every tile maps every other tile's slab: the mailboxes are all-to-all, the fields are
-  // only touched on the four neighbours
+  // only touched on the eight neighbours
   CommDev hd;
   memset(&hd, 0, sizeof hd);
   hd.nranks = c->nranks; hd.rank = c->rank;
+  const long long me = (long long)getpid();
   for (int r = 0; r < c->nranks; r++) {
     if (blobs[r].rank != r) return tl_fail(c, TL_ERR_ARG, "tl_comm_connect: blobs are not in rank order");
     if (r == c->rank) { hd.mail[r] = c->mail; continue; }
-    CU(c, cudaIpcOpenMemHandle(&c->rank_slab[r], blobs[r].handle, cudaIpcMemLazyEnablePeerAccess));
+    if (blobs[r].pid == me) {
+      // a tile of this very process (several tiles driven by threads, possibly on ONE GPU: the
+      // single-GPU test harness): its allocation is addressable as it is
+      if (blobs[r].device != c->device) {
+        cudaError_t pe = cudaDeviceEnablePeerAccess(blobs[r].device, 0);
+        if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (pe != cudaSuccess) return tl_fail(c, TL_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", blobs[r].device, cudaGetErrorString(pe));
+      }
+      c->rank_slab[r] = (void *)(uintptr_t)blobs[r].slab_ptr;
+      c->rank_ipc[r] = false;
+    } else {
+      CU(c, cudaIpcOpenMemHandle(&c->rank_slab[r], blobs[r].handle, cudaIpcMemLazyEnablePeerAccess));
+      c->rank_ipc[r] = true;
+    }
     hd.mail[r] = (MailSlot *)((char *)c->rank_slab[r] + blobs[r].mail_offset);
   }
   CU(c, cudaMemcpy(c->d_comm, &hd, sizeof hd, cudaMemcpyHostToDevice));
+  for (int r = 0; r < c->nranks; r++) c->rank_blob[r] = blobs[r];
   for (int s = 0; s < 4; s++) {
     const int nr = c->nbr_rank[s];
     if (nr < 0) continue;
     c->peer_blob[s] = blobs[nr];
     c->peer_slab[s] = c->rank_slab[nr];
   }
+  // NCCL serves the legacy mode (comm_fused = 0) only; without an id the context is fused-only
+  if (id128) {
 #ifdef TL_WITH_NCCL
-  ncclUniqueId id;
-  memcpy(&id, id128, 128);
-  if (!nccl_api().ok) return tl_fail(c, TL_ERR_COMM, "libnccl.so.2 could not be loaded");
-  ncclResult_t r = nccl_api().CommInitRank(&c->nccl, c->nranks, id, c->rank);
-  if (r != ncclSuccess) return tl_fail(c, TL_ERR_COMM, "ncclCommInitRank: %s", nccl_api().GetErrorString(r));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    if (!nccl_api().ok) return tl_fail(c, TL_ERR_COMM, "libnccl.so.2 could not be loaded");
+    ncclResult_t r = nccl_api().CommInitRank(&c->nccl, c->nranks, id, c->rank);
+    if (r != ncclSuccess) return tl_fail(c, TL_ERR_COMM, "ncclCommInitRank: %s", nccl_api().GetErrorString(r));
 #else
-  return tl_fail(c, TL_ERR_COMM, "library built without NCCL");
+    return tl_fail(c, TL_ERR_COMM, "library built without NCCL");
 #endif
+  }
   c->comm_ready = true;
   return TL_OK;
+}
+
+// All-tiles sum of n doubles through the peer-mapped mailboxes (tl_tile_exchange): one small
+// kernel, ~2 us, no library call -- what the fused mode uses outside the solver kernels (init,
+// summaries, rendezvous).  Everything earlier kernels of this stream wrote (peer stores
+// included) is ordered before the mailbox stores by the fence.sys + bar.sync at the start.
+__global__ void k_tile_allreduce(const CommDev *cd, SolveState *st, const double *src, double *dst, int n) {
+  __shared__ double sm[32];
+  if (st->comm_error) return;
+  if (threadIdx.x == blockDim.x - 1) __threadfence_system();
+  for (int q = 0; q < n; q++) {
+    const double v = (threadIdx.x == 0) ? src[q] : 0.0;
+    const double t = tl_tile_exchange(cd, st, v, sm);
+    if (threadIdx.x == 0) dst[q] = t;
+  }
 }
 
 // sum over tiles of n doubles living in device memory (stream ordered); out of place when
@@ -463,7 +502,14 @@ static int allreduce2(tl_ctx *c, const double *src, double *dst, int n) {
     return TL_OK;
   }
   if (!c->comm_ready) return tl_fail(c, TL_ERR_STATE, "tile context used before tl_comm_connect");
+  if (c->comm_fused) {
+    k_tile_allreduce<<<1, 32, 0, c->stream>>>(c->d_comm, c->st, src, dst, n);
+    c->launches++;
+    CHECK_LAUNCH(c);
+    return TL_OK;
+  }
 #ifdef TL_WITH_NCCL
+  if (!c->nccl) return tl_fail(c, TL_ERR_STATE, "comm_fused = 0 needs NCCL: tl_comm_connect was called without an NCCL id");
   ncclResult_t r = nccl_api().AllReduce(src, dst, n, ncclDouble, ncclSum, c->nccl, c->stream);
   if (r != ncclSuccess) return tl_fail(c, TL_ERR_COMM, "ncclAllReduce: %s", nccl_api().GetErrorString(r));
   return TL_OK;

@@ -67,9 +67,11 @@ class DeviceChunk:
         self._ck(self._l.tl_comm_unique_id(buf))
         return buf.raw
 
-    def comm_connect(self, blobs, nccl_id: bytes):
+    def comm_connect(self, blobs, nccl_id: bytes | None = None):
+        """Wire this tile to the others.  `nccl_id` (from rank 0's `comm_unique_id`) is only needed
+        for the legacy mode (option comm_fused = 0); None gives a fused-only context."""
         allb = b"".join(blobs)
-        self._ck(self._l.tl_comm_connect(self.ctx, C.c_char_p(allb), C.c_char_p(nccl_id)))
+        self._ck(self._l.tl_comm_connect(self.ctx, C.c_char_p(allb), C.c_char_p(nccl_id) if nccl_id else None))
 
     # ---- field transfer ----
     def set_field(self, name: str, arr: np.ndarray):

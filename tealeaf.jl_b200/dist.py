@@ -18,9 +18,88 @@ from .chunk import HostGeometry, paint_states
 from .settings import Settings
 
 
-def grid_for(world: int):
+class ThreadGroup:
+    """`torch.distributed` look-alike for `world` tiles driven by `world` THREADS of one process
+    (each thread calls `bind(rank)` first).  The tiles may live on different GPUs of the process
+    or all on ONE GPU: their kernels run concurrently on per-tile streams and meet in the same
+    peer-mapped mailboxes as on NVLink.  This is how the tiled code paths (halo pushes, mailbox
+    sums, depth-k PPCG) are tested on a single-GPU box; it is a test harness, not a product mode
+    (co-resident tiles share the GPU's bandwidth)."""
+    same_process = True
+
+    def __init__(self, world: int, grid=None):
+        import threading
+        self.world = world
+        self.grid = grid
+        self._barrier = threading.Barrier(world)
+        self._slots = [None] * world
+        self._local = threading.local()
+
+    def bind(self, rank: int):
+        self._local.rank = rank
+
+    def get_rank(self):
+        return self._local.rank
+
+    def get_world_size(self):
+        return self.world
+
+    def barrier(self):
+        self._barrier.wait()
+
+    def all_gather_object(self, out, obj):
+        self._slots[self.get_rank()] = obj
+        self._barrier.wait()
+        out[:] = list(self._slots)
+        self._barrier.wait()
+
+    def broadcast_object_list(self, lst, src=0):
+        if self.get_rank() == src:
+            self._slots[src] = list(lst)
+        self._barrier.wait()
+        lst[:] = list(self._slots[src])
+        self._barrier.wait()
+
+    def gather_object(self, obj, parts, dst=0):
+        self._slots[self.get_rank()] = obj
+        self._barrier.wait()
+        if self.get_rank() == dst:
+            parts[:] = list(self._slots)
+        self._barrier.wait()
+
+    def run(self, fn):
+        """Run `fn(rank)` on one thread per tile; returns the list of results, re-raises the
+        first exception (after breaking the barrier so the other threads do not wait forever)."""
+        import threading
+        results, errors = [None] * self.world, [None] * self.world
+
+        def work(r):
+            self.bind(r)
+            try:
+                results[r] = fn(r)
+            except BaseException as exc:  # noqa: BLE001 - reported to the caller below
+                errors[r] = exc
+                self._barrier.abort()
+
+        threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(self.world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        real = [e for e in errors if e is not None and e.__class__.__name__ != "BrokenBarrierError"]
+        if real or any(errors):
+            raise (real or [e for e in errors if e is not None])[0]
+        return results
+
+
+def grid_for(world: int, dist=None):
     """px x py for `world` ranks: 1x1, 1x2, 2x2, 2x4, else the squarest split."""
     import os
+    if dist is not None and getattr(dist, "grid", None):
+        px, py = dist.grid
+        if px * py != world:
+            raise ValueError(f"grid {px}x{py} does not match {world} tiles")
+        return px, py
     env = os.environ.get("TEALEAF_GRID")          # e.g. "1x4": override (tests, experiments)
     if env:
         px, py = (int(v) for v in env.lower().split("x"))
@@ -93,6 +172,9 @@ def connect(chunk, dist):
     world = dist.get_world_size()
     blobs = [None] * world
     dist.all_gather_object(blobs, chunk.comm_export())
+    if getattr(dist, "same_process", False):
+        chunk.comm_connect(blobs, None)          # NCCL cannot put two ranks on one GPU; fused mode needs none
+        return
     ident = [chunk.comm_unique_id() if dist.get_rank() == 0 else None]
     dist.broadcast_object_list(ident, src=0)
     chunk.comm_connect(blobs, ident[0])
@@ -102,7 +184,7 @@ def create_tile(settings: Settings, dist, device: int, backend=None, options=Non
     """`initialiseapp!` for this rank's tile.  Returns (chunk, geom, (px, py))."""
     from .app import upload_initial_state
     world, rank = dist.get_world_size(), dist.get_rank()
-    px, py = grid_for(world)
+    px, py = grid_for(world, dist)
     x0, y0, tnx, tny = tile_of(rank, px, py, settings.xcells, settings.ycells)
     if backend is None:
         from .device import DeviceChunk
@@ -120,7 +202,7 @@ def gather_field(chunk, name: str, settings: Settings, dist, dst: int = 0):
     """Assemble the global (x, y) array of `name` (interior from every tile; halos from the
     tiles that own the physical boundary) on rank `dst`."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    px, py = grid_for(world)
+    px, py = grid_for(world, dist)
     local = chunk.get_field(name)
     parts = [None] * world if rank == dst else None
     dist.gather_object(local, parts, dst=dst)

@@ -1,0 +1,94 @@
+"""Tiled (2-D domain decomposition) solves on ONE GPU: N tiles driven by N threads of this process
+(`tealeaf_jl_b200.dist.ThreadGroup`), all on cuda:0.  Their kernels run concurrently on per-tile
+streams and use exactly the multi-GPU data path -- edge cells stored into the neighbour tiles'
+halo cells, dot products summed through the peer-mapped mailboxes in the kernel tails, depth-k
+PPCG groups -- so the decomposition logic is covered by the single-GPU `-m gpu` run as well
+(tests/test_multi_gpu.py repeats it across real GPUs when the box has several).
+
+Every case is checked against the single-chunk CPU oracle with the north-star bar: identical
+iteration counts (CG: +-1), per-step summaries within 1e-10, u / energy within 1e-9."""
+import numpy as np
+import pytest
+
+import tealeaf_jl_b200 as tl
+from tealeaf_jl_b200 import dist as tld
+from conftest import classic_settings
+
+pytestmark = pytest.mark.gpu
+
+
+def run_tiled(grid, solver, nx, ny, steps=1, over=None, options=None, fields=("u", "energy")):
+    """Solve the classic deck tiled `grid` = (px, py) on cuda:0.  Returns rank 0's
+    (records, per-step summaries, {field: assembled global array})."""
+    over = over or {}
+    world = grid[0] * grid[1]
+    tg = tld.ThreadGroup(world, grid)
+
+    def fn(rank):
+        s = classic_settings(nx, ny=ny, steps=steps, solver=solver, **over)
+        chunk, geom, _ = tld.create_tile(s, tg, 0, options=options)
+        try:
+            summaries = []
+            recs, final = tl.diffuse(chunk, s, geom,
+                                     on_step=lambda rec: summaries.append(chunk.fieldsummary(geom.cell_volume)))
+            out = {f: tld.gather_field(chunk, f, s, tg) for f in fields}
+        finally:
+            try:
+                tg.barrier()      # nobody frees memory a neighbour's kernel may still address
+            except Exception:
+                pass
+            chunk.close()
+        return recs, summaries, out
+
+    return tg.run(fn)[0]
+
+
+def run_oracle(solver, nx, ny, steps=1, over=None):
+    from oracle.oracle import OracleChunk
+    s = classic_settings(nx, ny=ny, steps=steps, solver=solver, **(over or {}))
+    oc, og = tl.initialiseapp(s, backend=OracleChunk)
+    summaries = []
+    recs, final = tl.diffuse(oc, s, og, on_step=lambda rec: summaries.append(oc.fieldsummary(og.cell_volume)))
+    return recs, summaries, {"u": oc.get_field("u"), "energy": oc.get_field("energy")}
+
+
+def check_against_oracle(got, ref, solver, hd=2):
+    recs, sums, fields = got
+    orecs, osums, ofields = ref
+    its, oits = [r["iters"] for r in recs], [r["iters"] for r in orecs]
+    slack = 1 if solver == "cg" else 0
+    assert all(abs(a - b) <= slack for a, b in zip(its, oits)), (its, oits)
+    serr = max(abs(a / b - 1) for sa, sb in zip(sums, osums) for a, b in zip(sa, sb))
+    assert serr < 1e-10, serr
+    for f in ("u", "energy"):
+        a, b = fields[f][hd:-hd, hd:-hd], ofields[f][hd:-hd, hd:-hd]
+        err = np.abs(a - b).max() / np.abs(b).max()
+        assert err < 1e-9, (f, err)
+
+
+CASES = [
+    # grid, solver, nx, ny, settings overrides
+    ((1, 2), "cg", 256, 192, {}),
+    ((2, 1), "cg", 130, 77, {}),
+    ((2, 2), "cg", 200, 150, {}),
+    ((1, 2), "cheby", 192, 256, {}),
+    ((2, 2), "cheby", 129, 67, {}),
+    ((1, 2), "ppcg", 192, 160, {"ppcginnersteps": 6}),
+    ((2, 2), "ppcg", 131, 150, {"ppcginnersteps": 5}),
+    ((2, 2), "jacobi", 160, 130, {"maxiters": 120}),
+    ((1, 4), "cg", 96, 256, {}),
+    ((4, 1), "ppcg", 300, 64, {"ppcginnersteps": 4}),
+]
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("grid,solver,nx,ny,over", CASES, ids=[f"{g[0]}x{g[1]}-{s}-{nx}x{ny}" for g, s, nx, ny, _ in CASES])
+def test_tiles_on_one_gpu_match_oracle(grid, solver, nx, ny, over):
+    got = run_tiled(grid, solver, nx, ny, steps=1, over=over)
+    check_against_oracle(got, run_oracle(solver, nx, ny, steps=1, over=over), solver)
+
+
+@pytest.mark.timeout(600)
+def test_two_timesteps_tiled():
+    got = run_tiled((2, 2), "cg", 160, 160, steps=2)
+    check_against_oracle(got, run_oracle("cg", 160, 160, steps=2), "cg")
