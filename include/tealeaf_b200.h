@@ -61,7 +61,7 @@ typedef struct tl_solve_info {
   int cheby_iters;   /* Chebyshev iterations (Cheby) or PPCG outer iterations (PPCG) */
   int est_iters;     /* Cheby.calciter estimate (Cheby.jl:109-118) */
   int inner_total;   /* PPCG inner steps executed */
-  int reserved;
+  int halo_depth_k;  /* PPCG: exchange depth the inner steps used (1 on a single tile) */
   double error;      /* final `error` (rr) */
   double eigmin, eigmax;
   double solve_ms;   /* device time of the solve, CUDA events on the solve stream */
@@ -160,9 +160,15 @@ int tl_cg_solve(tl_ctx *ctx, int coefficient, double rx, double ry, double eps, 
 /* Cheby.solve!, src/solvers/Cheby.jl:10-61 */
 int tl_cheby_solve(tl_ctx *ctx, int coefficient, double rx, double ry, double eps, int max_iters,
                    int presteps, double epslim, int errorswitch, tl_solve_info *info);
-/* PPCG.solve!, src/solvers/PPCG.jl:9-55 */
+/* PPCG.solve!, src/solvers/PPCG.jl:9-55.  halo_depth_k (0..halo_depth; 0 = automatic, i.e. the
+ * option "ppcg_halo_depth", which defaults to halo_depth) is the depth of the sd/r halo exchange
+ * between tiles: the inner steps of PPCG.jl:75-84 run in groups of halo_depth_k with ONE exchange
+ * per group (matrix-powers kernel: step q of a group also computes k-1-q cells into the
+ * tile-internal halos, redundantly and bit-identically to the owning tile).  The result does not
+ * depend on it bit for bit; a single chunk exchanges nothing and ignores it. */
 int tl_ppcg_solve(tl_ctx *ctx, int coefficient, double rx, double ry, double eps, int max_iters,
-                  int presteps, double epslim, int errorswitch, int inner_steps, tl_solve_info *info);
+                  int presteps, double epslim, int errorswitch, int inner_steps, int halo_depth_k,
+                  tl_solve_info *info);
 
 /* Jacobi.driver! -- the module's solve!, src/solvers/Jacobi.jl:7-31 */
 int tl_jacobi_solve(tl_ctx *ctx, int coefficient, double rx, double ry, double eps, int max_iters,

@@ -23,7 +23,7 @@ const FIELD_ID = Dict(:density => 0, :energy0 => 1, :energy => 2, :u => 3, :u0 =
 
 # tl_solve_info
 struct SolveInfo
-    iters::Cint; cg_iters::Cint; cheby_iters::Cint; est_iters::Cint; inner_total::Cint; reserved::Cint
+    iters::Cint; cg_iters::Cint; cheby_iters::Cint; est_iters::Cint; inner_total::Cint; halo_depth_k::Cint
     error::Cdouble; eigmin::Cdouble; eigmax::Cdouble; solve_ms::Cdouble; kernel_launches::Clonglong
 end
 
@@ -172,9 +172,9 @@ using TeaLeaf
 function solve!(chunk::B200Chunk, set::Settings, rx::Float64, ry::Float64)
     info = Ref{SolveInfo}()
     check(chunk, ccall((:tl_ppcg_solve, LIB), Cint,
-                       (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Cint, Ref{SolveInfo}),
+                       (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Cint, Cint, Ref{SolveInfo}),
                        chunk.ctx, set.coefficient, rx, ry, set.eps, set.maxiters, set.presteps, set.epslim,
-                       set.errorswitch, set.ppcginnersteps, info))
+                       set.errorswitch, set.ppcginnersteps, 0 #= halo_depth_k: automatic = set.halodepth =#, info))
     resettoexchange!(set); set.toexchange[:p] = true
     chunk.eigmin, chunk.eigmax = info[].eigmin, info[].eigmax
     iters, error = info[].iters, info[].error

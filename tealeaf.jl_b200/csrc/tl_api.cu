@@ -28,7 +28,9 @@
 #define TL_ERROR_SWITCH_MAX 1.0   // src/kernels.jl:8
 #define TL_CGEIGENITERS 20        // src/solvers/Cheby.jl:7
 
-enum { B_P1 = TL_NUM_FIELDS, B_U1, B_SD1, B_COUNT };  // ping-pong partners of p, u, sd
+// ping-pong partners of p, u, sd; the working buffers of the matrix-powers PPCG groups
+// (PpcgDkParams: sd wa/wb, the second group-input copy of r, r's working buffer)
+enum { B_P1 = TL_NUM_FIELDS, B_U1, B_SD1, B_SD2, B_SD3, B_R1, B_R2, B_COUNT };
 
 #ifdef TL_WITH_NCCL
 // NCCL is bound lazily with dlopen instead of at link time: a process that also imports torch
@@ -95,8 +97,11 @@ struct tl_ctx {
   int l2_persist_field = TL_R;
   Tiling tiling{}, pw_tiling{};   // stencil kernels / pointwise kernels
   int fused_grid = 0, pw_grid = 0, basic_grid = 0;
+  DkExt dk_ext{};                 // k_ppcg_inner_dk: the extension warps appended to `tiling`
+  int dk_grid = 0, dk_k = 1, dk_rows_per_chunk = 0;
+  int ppcg_depth_k = 0;           // option "ppcg_halo_depth": 0 = auto (halo_depth)
   cudaGraphExec_t g_cg = nullptr, g_cheby = nullptr, g_ppcg = nullptr, g_jacobi = nullptr;
-  int g_cg_iters = 0, g_cheby_iters = 0, g_ppcg_iters = 0, g_ppcg_inner = 0, g_jacobi_iters = 0;
+  int g_cg_iters = 0, g_cheby_iters = 0, g_ppcg_iters = 0, g_ppcg_inner = 0, g_ppcg_k = 0, g_jacobi_iters = 0;
   long long launches = 0;
   // peers (tile-internal sides): 0 left, 1 right, 2 bottom, 3 top
   int nbr_rank[4] = {-1, -1, -1, -1};
@@ -210,6 +215,27 @@ static void compute_tiling(tl_ctx *c) {
   const long cells = (long)(g.nx + 2 * g.hd) * (g.ny + 2 * g.hd);
   long nb = (cells + TL_BASIC_THREADS - 1) / TL_BASIC_THREADS;
   c->basic_grid = (int)std::max(1L, std::min<long>(nb, (long)c->num_sms * 8));
+}
+
+// Decomposition of the tile extended by k-1 cells towards its neighbour tiles (k_ppcg_inner_dk):
+// the plain kernels' warps for the interior plus appended warps for the extension
+// (tl_march_setup_ext).
+static void compute_dk_tiling(tl_ctx *c, int k) {
+  const Geo &g = c->g;
+  const int wpb = TL_FUSED_THREADS / 32;
+  const Tiling &t = c->tiling;
+  DkExt x;
+  x.emax = k - 1;
+  x.left = !(g.phys & TL_PHYS_LEFT);
+  x.right = !(g.phys & TL_PHYS_RIGHT) && (t.nstrips * TL_STRIP < g.nx + x.emax);
+  x.bottom = !(g.phys & TL_PHYS_BOTTOM);
+  x.top = !(g.phys & TL_PHYS_TOP);
+  const int nall = t.nstrips + x.left + x.right;
+  const int warps = t.nstrips * t.nchunks + nall * (x.bottom + x.top) + t.nchunks * (x.left + x.right);
+  c->dk_k = k;
+  c->dk_ext = x;
+  c->dk_rows_per_chunk = t.rows_per_chunk;
+  c->dk_grid = (warps + wpb - 1) / wpb;   // <= 4 * TL_MAX_GRID partial slots exist and one value is summed
 }
 
 // Optional L2 residency: marks (part of) one field as persisting in the 126 MB L2 through the
@@ -374,6 +400,10 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "b_reverse") c->b_reverse = value != 0.0;
   else if (n == "comm_fused") c->comm_fused = value != 0.0;
   else if (n == "use_pdl") c->use_pdl = value != 0.0;
+  else if (n == "ppcg_halo_depth") {   // exchange depth of the PPCG inner steps on tiles: 0 = auto (halo_depth)
+    if (value < 0 || value > c->g.hd) return tl_fail(c, TL_ERR_ARG, "ppcg_halo_depth must be in 0..halo_depth");
+    c->ppcg_depth_k = (int)value;
+  }
   else if (n == "l2_persist_mb") c->l2_persist_mb = value;
   else if (n == "l2_hit_scale") c->l2_hit_scale = value;
   else if (n == "l2_persist_field") c->l2_persist_field = std::min(std::max(0, (int)value), (int)B_COUNT - 1);
@@ -386,6 +416,7 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   cudaStreamSynchronize(c->stream);
   destroy_graphs(c);
   compute_tiling(c);
+  c->dk_grid = 0;   // recomputed by the next depth-k PPCG solve
   return apply_l2_policy(c);
 }
 
@@ -540,6 +571,24 @@ static Push push_for(tl_ctx *c, int bufidx) {
   }
   return p;
 }
+// depth-k halo targets of buffer `bufidx` on the eight surrounding tiles
+static Push8 push8_for(tl_ctx *c, int bufidx) {
+  Push8 p;
+  memset(&p, 0, sizeof p);
+  if (c->nranks == 1 || !c->comm_fused) return p;
+  for (int dy = -1; dy <= 1; dy++)
+    for (int dx = -1; dx <= 1; dx++) {
+      const int tx = c->cx + dx, ty = c->cy + dy;
+      if ((dx == 0 && dy == 0) || tx < 0 || tx >= c->px || ty < 0 || ty >= c->py) continue;
+      const int r = tx + ty * c->px;
+      if (!c->rank_slab[r]) continue;
+      const CommBlob &b = c->rank_blob[r];
+      PushSide &t = p.s[(dy + 1) * 3 + (dx + 1)];
+      t.f0 = (double *)((char *)c->rank_slab[r] + b.buf_offset[bufidx]);
+      t.pitch = b.pitch; t.nx = b.nx; t.ny = b.ny;
+    }
+  return p;
+}
 static const CommDev *comm_dev(tl_ctx *c) { return (c->nranks > 1 && c->comm_fused) ? c->d_comm : nullptr; }
 static bool legacy_comm(tl_ctx *c) { return c->nranks > 1 && !c->comm_fused; }
 
@@ -560,6 +609,27 @@ static int pull_halo(tl_ctx *c, int bufidx, int depth) {
                                            peer_face(c, 1, bufidx), peer_face(c, 2, bufidx), peer_face(c, 3, bufidx));
   c->launches++;
   CHECK_LAUNCH(c);
+  return TL_OK;
+}
+
+static int tile_barrier(tl_ctx *c);
+// tile-internal halos of buffer `bufidx`, `depth` cells deep INCLUDING the corner blocks (two
+// phases with a rendezvous in between; see k_pull_halo_wide).  The caller guarantees the
+// neighbours' interiors are final; ends with a rendezvous.
+static int pull_halo_wide(tl_ctx *c, const int *bufs, int nbufs, int depth) {
+  if (c->nranks == 1) return TL_OK;
+  for (int phase = 0; phase < 2; phase++) {
+    const int total = 2 * depth * (phase == 0 ? c->g.ny : c->g.nx + 2 * depth);
+    const int grid = std::max(1, std::min((total + 255) / 256, c->num_sms * 4));
+    for (int q = 0; q < nbufs; q++) {
+      const int b = bufs[q];
+      k_pull_halo_wide<<<grid, 256, 0, c->stream>>>(c->g, depth, phase, c->buf[b], peer_face(c, 0, b), peer_face(c, 1, b),
+                                                    peer_face(c, 2, b), peer_face(c, 3, b));
+      c->launches++;
+      CHECK_LAUNCH(c);
+    }
+    TRY(tile_barrier(c));
+  }
   return TL_OK;
 }
 
@@ -1222,7 +1292,51 @@ static PpcgUrParams ppcg_ur_params(tl_ctx *c) {
   P.p0 = c->buf[TL_P]; P.p1 = c->buf[B_P1]; P.w = c->buf[TL_W]; P.u = c->buf[TL_U]; P.r = c->buf[TL_R];
   P.sd0 = c->buf[TL_SD];
   P.partials = c->partials; P.cd = comm_dev(c); P.push_sd0 = push_for(c, TL_SD);
+  P.deep = 0; P.r_out = P.r; P.d_sd = 1; P.d_r = 0;
+  memset(&P.push_sd8, 0, sizeof P.push_sd8);
+  memset(&P.push_r8, 0, sizeof P.push_r8);
   return P;
+}
+// the matrix-powers variant: r goes to the first group's input copy, halos k (sd) / k-1 (r) deep
+static PpcgUrParams ppcg_ur_params_dk(tl_ctx *c, int inner_steps, int k) {
+  PpcgUrParams P = ppcg_ur_params(c);
+  const int G = (inner_steps + k - 1) / k, L0 = std::min(k, inner_steps);
+  P.deep = 1;
+  P.r_out = c->buf[(G & 1) ? B_R1 : TL_R];
+  P.d_sd = L0; P.d_r = L0 - 1;
+  P.push_sd8 = push8_for(c, TL_SD);
+  P.push_r8 = push8_for(c, (G & 1) ? B_R1 : TL_R);
+  return P;
+}
+static PpcgDkParams ppcg_dk_params(tl_ctx *c) {
+  PpcgDkParams P;
+  P.g = c->g; P.t = c->tiling; P.ext = c->dk_ext; P.st = c->st; P.alphas = c->ch_alphas; P.betas = c->ch_betas;
+  P.sin0 = c->buf[TL_SD]; P.sin1 = c->buf[B_SD1]; P.wa = c->buf[B_SD2]; P.wb = c->buf[B_SD3];
+  P.rin0 = c->buf[TL_R]; P.rin1 = c->buf[B_R1]; P.rw = c->buf[B_R2];
+  P.u = c->buf[TL_U]; P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
+  P.cd = comm_dev(c); P.k = c->dk_k;
+  P.push_sin0 = push8_for(c, TL_SD); P.push_sin1 = push8_for(c, B_SD1);
+  P.push_rin0 = push8_for(c, TL_R); P.push_rin1 = push8_for(c, B_R1);
+  return P;
+}
+template <int S, int MINB>
+static int launch_ppcg_dk_ring(tl_ctx *c, const PpcgDkParams &P) {
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_ppcg_inner_dk<S, MINB>, smem, &prepared));
+  CU(c, tl_launch(c, k_ppcg_inner_dk<S, MINB>, c->dk_grid, TL_FUSED_THREADS, smem, P));
+  return TL_OK;
+}
+static int launch_ppcg_dk(tl_ctx *c) {
+  const PpcgDkParams P = ppcg_dk_params(c);
+  switch (c->ring_eff) {
+    case 3: TRY((launch_ppcg_dk_ring<3, 3>(c, P))); break;
+    case 4: TRY((launch_ppcg_dk_ring<4, 2>(c, P))); break;
+    case 6: TRY((launch_ppcg_dk_ring<6, 1>(c, P))); break;
+    default: return tl_fail(c, TL_ERR_STATE, "internal: ring depth %d", c->ring_eff);
+  }
+  CHECK_LAUNCH(c);
+  return TL_OK;
 }
 static PpcgInnerParams ppcg_inner_params(tl_ctx *c) {
   PpcgInnerParams P;
@@ -1238,8 +1352,16 @@ static PpcgInnerParams ppcg_inner_params(tl_ctx *c) {
 // reads through the stencil (p'; sd0; sd'; r after the last inner step) and ends with the tile
 // exchange.  Legacy mode: depth-1 halo pulls -- r, p before the matvec (ordered by the preceding rr
 // allreduce) and sd before every inner step (ordered by a 1-double NCCL rendezvous).
-static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps) {
+static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k) {
   const bool legacy = legacy_comm(c);
+  if (depth_k > 1) {
+    // matrix-powers groups: one tile exchange per depth_k inner steps (PpcgDkParams)
+    TRY(launch_cg_a<false>(c));
+    CU(c, tl_launch(c, k_ppcg_ur_sd, c->pw_grid, TL_FUSED_THREADS, 0, ppcg_ur_params_dk(c, inner_steps, depth_k)));
+    for (int pp = 0; pp < inner_steps; pp++) TRY(launch_ppcg_dk(c));
+    c->launches += 2 + inner_steps;
+    return TL_OK;
+  }
   if (legacy) {
     TRY(pull_halo(c, TL_R, 1));
     TRY(pull_halo(c, TL_P, 1));
@@ -1261,11 +1383,27 @@ static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps) {
   return TL_OK;
 }
 
+// Exchange depth the inner steps of this context will use: the request (0 = the option
+// "ppcg_halo_depth", whose 0 = halo_depth) limited to what the halo ring and the smallest tile
+// can carry; 1 on a single tile and in the legacy communication mode.
+static int ppcg_effective_depth(tl_ctx *c, int requested, int inner_steps) {
+  if (c->nranks == 1 || !c->comm_fused) return 1;
+  int k = requested > 0 ? requested : (c->ppcg_depth_k > 0 ? c->ppcg_depth_k : c->g.hd);
+  k = std::min(k, c->g.hd);
+  k = std::min(k, inner_steps);
+  for (int r = 0; r < c->nranks; r++) k = std::min(k, std::min(c->rank_blob[r].nx, c->rank_blob[r].ny));
+  return std::max(k, 1);
+}
+
 extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double eps, int max_iters, int presteps,
-                             double epslim, int errorswitch, int inner_steps, tl_solve_info *info) {
-  if (!c || !info || inner_steps < 1) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_solve: bad argument");
+                             double epslim, int errorswitch, int inner_steps, int halo_depth_k, tl_solve_info *info) {
+  if (!c || !info || inner_steps < 1 || halo_depth_k < 0) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_solve: bad argument");
+  if (halo_depth_k > c->g.hd) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_solve: halo_depth_k %d exceeds halo_depth %d", halo_depth_k, c->g.hd);
   memset(info, 0, sizeof *info);
   CU(c, cudaSetDevice(c->device));
+  if (c->nranks > 1 && !c->comm_ready) return tl_fail(c, TL_ERR_STATE, "tile context used before tl_comm_connect");
+  const int depth_k = ppcg_effective_depth(c, halo_depth_k, inner_steps);
+  info->halo_depth_k = depth_k;
   max_iters = std::min(max_iters, c->max_iters);
   const long long l0 = c->launches;
   CU(c, cudaEventRecord(c->ev_start, c->stream));
@@ -1300,14 +1438,26 @@ extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double e
   k_state_begin<<<1, 1, 0, c->stream>>>(c->st, cfg, cgit, theta, inner_steps);
   c->launches++;
   CHECK_LAUNCH(c);
-  auto enq = [&]() { return enqueue_ppcg_outer(c, inner_steps); };
+  if (depth_k > 1) {
+    // the groups compute in the tile-internal halos: kx, ky are needed there, depth_k cells deep,
+    // corner blocks included (CG.init! leaves them only partly defined, CG.jl:61-68)
+    const int kbufs[2] = {TL_KX, TL_KY};
+    TRY(tile_barrier(c));
+    TRY(pull_halo_wide(c, kbufs, 2, depth_k));
+    if (c->dk_k != depth_k || c->dk_grid == 0 || c->dk_rows_per_chunk != c->tiling.rows_per_chunk) {
+      compute_dk_tiling(c, depth_k);
+      if (c->g_ppcg) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
+    }
+  }
+  auto enq = [&]() { return enqueue_ppcg_outer(c, inner_steps, depth_k); };
   auto stop = [&](const SolveState &s) { return tl_should_stop(s.iter, s.red_rr, s.cfg); };
   const int chunk = std::max(1, c->graph_iters / 4);
-  if (c->g_ppcg && c->g_ppcg_inner != inner_steps) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
+  if (c->g_ppcg && (c->g_ppcg_inner != inner_steps || c->g_ppcg_k != depth_k)) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
   c->g_ppcg_inner = inner_steps;
+  c->g_ppcg_k = depth_k;
   TRY(run_chunks(c, &c->g_ppcg, &c->g_ppcg_iters, chunk, 2 + inner_steps, enq, stop, &fin));
   TRY(cg_flush(c, fin.iter, false));
-  c->sd_cur = inner_steps & 1;
+  c->sd_cur = (depth_k > 1 ? (inner_steps + depth_k - 1) / depth_k : inner_steps) & 1;
   if (c->sd_cur) {
     LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[B_SD1], c->buf[TL_SD]);
     c->sd_cur = 0;

@@ -90,6 +90,10 @@ struct CommDev {
 // tile-internal side (0 left, 1 right, 2 bottom, 3 top); f0 = interior origin, null on physical sides.
 struct PushSide { double *f0; int pitch, nx, ny; };
 struct Push { PushSide s[4]; };
+// Depth-k exchanges (matrix-powers PPCG) also fill the corner blocks of the halo, so they address
+// all EIGHT surrounding tiles: index (dy+1)*3 + (dx+1), dx/dy in {-1,0,1}; entry 4 (the tile
+// itself) is unused; f0 is null where there is no tile.
+struct Push8 { PushSide s[9]; };
 
 __host__ __device__ inline bool tl_should_stop(int it, double rr, const StopCfg &c) {
   if (it >= c.max_iters) return true;

@@ -305,6 +305,30 @@ __global__ void k_pull_halo(Geo g, int depth, double *f, PeerFace left, PeerFace
   }
 }
 
+// Depth-`depth` halo INCLUDING the corner blocks, in the classic two phases (a rendezvous of all
+// tiles between them): phase 0 fills the left/right halo columns of the interior rows, phase 1 the
+// bottom/top halo rows over the full width [-depth, nx+depth) -- the neighbour's own left/right
+// halo columns (filled in its phase 0) carry the diagonal tiles' cells.  Used once per solve for
+// kx, ky of the matrix-powers PPCG groups.
+__global__ void k_pull_halo_wide(Geo g, int depth, int phase, double *f, PeerFace left, PeerFace right, PeerFace bottom,
+                                 PeerFace top) {
+  if (phase == 0) {
+    const int total = 2 * g.ny * depth;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+      const int side = t / (g.ny * depth), q = t % (g.ny * depth), j = q / depth, d = q % depth + 1;
+      if (side == 0) { if (left.f0)  f[(long)j * g.pitch - d] = __ldcv(&left.f0[(long)j * left.pitch + left.nx - d]); }
+      else           { if (right.f0) f[(long)j * g.pitch + g.nx + d - 1] = __ldcv(&right.f0[(long)j * right.pitch + d - 1]); }
+    }
+  } else {
+    const int wide = g.nx + 2 * depth, total = 2 * wide * depth;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+      const int side = t / (wide * depth), q = t % (wide * depth), d = q / wide + 1, i = q % wide - depth;
+      if (side == 0) { if (top.f0)    f[(long)(g.ny + d - 1) * g.pitch + i] = __ldcv(&top.f0[(long)(d - 1) * top.pitch + i]); }
+      else           { if (bottom.f0) f[(long)(-d) * g.pitch + i] = __ldcv(&bottom.f0[(long)(bottom.ny - d) * bottom.pitch + i]); }
+    }
+  }
+}
+
 // kernels.jl:119-133 (+ upstream vol/mass/ie): cell_mass = volume*density;
 // vol += volume; mass += cell_mass; ie += cell_mass*energy0; temp += cell_mass*u.
 __global__ void k_field_summary(Geo g, double cell_volume, const double *__restrict__ density,

@@ -65,6 +65,41 @@ __device__ __forceinline__ void tl_push_edges(const Push &ps, const Geo &g, cons
   }
 }
 
+// Depth-d variant for the matrix-powers PPCG groups: stores this lane's INTERIOR cells (i0, i0+1)
+// of interior row j into the halo cells of every surrounding tile (corner tiles included) whose
+// depth-d halo contains them.  ina / inb: cell i0 / i0+1 is an interior cell of this tile.
+// Rows of the bottom/top bands go out as whole 16-byte row segments, columns of the left/right
+// bands as 8-byte cells.  Same ordering argument as tl_push_edges (tl_tile_exchange).
+__device__ __forceinline__ void tl_push_deep(const Push8 &ps, const Geo &g, int d, int i0, bool ina, bool inb, int j,
+                                             double2 v) {
+  const bool yb = j < d, yt = j >= g.ny - d;
+  const bool xl = i0 < d, xr = i0 + 1 >= g.nx - d;
+  if (!(yb || yt || xl || xr) || !(ina || inb)) return;
+#pragma unroll
+  for (int dyi = 0; dyi < 3; dyi++) {
+    if ((dyi == 0 && !yb) || (dyi == 2 && !yt)) continue;
+#pragma unroll
+    for (int dxi = 0; dxi < 3; dxi++) {
+      if (dyi == 1 && dxi == 1) continue;
+      const PushSide &t = ps.s[dyi * 3 + dxi];
+      if (!t.f0) continue;
+      const int tj = (dyi == 1) ? j : (dyi == 0 ? t.ny + j : j - g.ny);
+      double *row = t.f0 + (long)tj * t.pitch;
+      if (dxi == 1) {
+        if (ina && inb) tl_st2(row + i0, v);
+        else if (ina) row[i0] = v.x;
+        else row[i0 + 1] = v.y;
+      } else if (dxi == 0) {
+        if (ina && i0 < d) row[t.nx + i0] = v.x;
+        if (inb && i0 + 1 < d) row[t.nx + i0 + 1] = v.y;
+      } else {
+        if (ina && i0 >= g.nx - d) row[i0 - g.nx] = v.x;
+        if (inb && i0 + 1 >= g.nx - d) row[i0 + 1 - g.nx] = v.y;
+      }
+    }
+  }
+}
+
 // Depth-1 reflective halo of one field as a write-through (haloupdate!, kernels.jl:191-210)
 __device__ __forceinline__ void tl_reflect_edges(double *f, const Geo &g, const MarchCtx &m, int j, long oc, double2 v) {
   if (!m.acta) return;
@@ -262,6 +297,12 @@ struct PpcgUrParams {
   double *partials;
   const CommDev *cd;
   Push push_sd0;
+  // depth-k groups (tl_kernels_ring.cuh, k_ppcg_inner_dk): r goes to the buffer the first group
+  // reads (r_out, may be r itself) and the first group's halos are pushed at depth d_sd / d_r
+  int deep;
+  double *r_out;
+  int d_sd, d_r;
+  Push8 push_sd8, push_r8;
 };
 
 __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_ppcg_ur_sd(const PpcgUrParams P) {
@@ -280,7 +321,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_ppcg_ur_sd(const PpcgUr
   MarchCtx m;
   if (tl_march_setup(g, P.t, m)) {
     for (int j = m.j0; j < m.j1; j++) {
-      double2 sv = make_double2(0.0, 0.0);
+      double2 sv = make_double2(0.0, 0.0), rv2 = make_double2(0.0, 0.0);
 #pragma unroll
       for (int c = 0; c < 2; c++) {
         const int i = m.i0 + c;
@@ -288,12 +329,15 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_ppcg_ur_sd(const PpcgUr
         const long o = (long)j * g.pitch + i;
         P.u[o] += alpha * p[o];
         const double rv = P.r[o] - alpha * P.w[o];
-        P.r[o] = rv;
+        if (P.deep) P.r_out[o] = rv; else P.r[o] = rv;
         const double s = rv / theta;
         P.sd0[o] = s;
-        if (c == 0) sv.x = s; else sv.y = s;
+        if (c == 0) { sv.x = s; rv2.x = rv; } else { sv.y = s; rv2.y = rv; }
       }
-      if (tiled) tl_push_edges(P.push_sd0, g, m, j, sv);
+      if (P.deep) {
+        tl_push_deep(P.push_sd8, g, P.d_sd, m.i0, m.acta, m.actb, j, sv);
+        if (P.d_r > 0) tl_push_deep(P.push_r8, g, P.d_r, m.i0, m.acta, m.actb, j, rv2);
+      } else if (tiled) tl_push_edges(P.push_sd0, g, m, j, sv);
     }
   }
   if (tiled) {   // the first inner step reads the neighbours' sd: completion barrier
@@ -314,6 +358,74 @@ struct PpcgInnerParams {
   const CommDev *cd;
   Push push_sda, push_sdb, push_r;
 };
+
+// Matrix-powers variant of the inner steps for tiles (k_ppcg_inner_dk): the steps are grouped by
+// k = the halo depth of the exchange.  A group starts with sd valid k cells deep in the
+// tile-internal halos (r: k-1 cells; kx, ky pulled once per solve), step q of the group computes
+// r, sd' on the tile EXTENDED by k-1-q cells towards its neighbour tiles (redundantly: the same
+// arithmetic on the same inputs as the owner, so bit-identical), and only the group's last step
+// pushes halos and meets the other tiles -- one exchange per k steps instead of one per step.
+// Buffers rotate so that a tile that runs ahead never writes what a neighbour may still read:
+//   sd: group g reads sin[g&1] in its first step and writes sin[(g+1)&1] (+ the neighbours'
+//       halos of it) in its last; the steps in between ping-pong between wa/wb;
+//   r : likewise rin[(G-g)&1] -> rw (in place in between) -> rin[(G-g-1)&1], G = number of
+//       groups, so that the last group leaves r in rin[0] = the Chunk's r.
+// The halos of wa/wb/rw are never written by another tile; those of sin/rin only at group ends,
+// and only the copy the receiving tile is not using before the next rendezvous.
+struct DkExt { int left, right, bottom, top, emax; };   // extra strips / chunks of the extension (0/1 each), k-1
+struct PpcgDkParams {
+  Geo g; Tiling t; DkExt ext;    // t: the plain kernels' decomposition of the interior; ext: tl_march_setup_ext
+  SolveState *st;
+  const double *alphas; const double *betas;
+  double *sin0; double *sin1; double *wa; double *wb;
+  double *rin0; double *rin1; double *rw;
+  double *u; const double *kx; const double *ky;
+  double *partials;
+  const CommDev *cd;
+  int k;                         // exchange depth (steps per group)
+  Push8 push_sin0, push_sin1, push_rin0, push_rin1;
+};
+
+// Work decomposition of the extended tile.  The interior keeps EXACTLY the warps of the plain
+// kernels (strip s, chunk q -> warp q*nstrips + s: same cells per warp, same warps per block, so
+// the dot product is summed in the same order and depth-k results equal depth-1 results bit for
+// bit); the extension is covered by extra warps appended after them: one chunk of emax rows
+// below / above the tile over all strips, and one 64-column strip left / right of the regular
+// ones over all regular chunks (the right one only if the last regular strip cannot hold the
+// extension).  The active window [xlo,xhi) x [ylo,yhi) of the current step masks the rest.
+__device__ __forceinline__ bool tl_march_setup_ext(const Geo &g, const Tiling &t, const DkExt &x, int xlo, int xhi, int ylo,
+                                                   int yhi, MarchCtx &m) {
+  m.lane = threadIdx.x & 31;
+  int wt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nreg = t.nstrips * t.nchunks;
+  int strip, r0, r1;
+  if (wt < nreg) {
+    strip = wt % t.nstrips;
+    const int q = wt / t.nstrips;
+    r0 = q * t.rows_per_chunk; r1 = min(g.ny, r0 + t.rows_per_chunk);
+  } else {
+    wt -= nreg;
+    const int nall = t.nstrips + x.left + x.right;
+    bool found = false;
+    strip = 0; r0 = r1 = 0;
+    if (x.bottom) { if (wt < nall) { strip = wt; r0 = -x.emax; r1 = 0; found = true; } else wt -= nall; }
+    if (!found && x.top) { if (wt < nall) { strip = wt; r0 = g.ny; r1 = g.ny + x.emax; found = true; } else wt -= nall; }
+    if (!found && x.left) { if (wt < t.nchunks) { strip = t.nstrips; r0 = wt * t.rows_per_chunk; r1 = min(g.ny, r0 + t.rows_per_chunk); found = true; } else wt -= t.nchunks; }
+    if (!found && x.right) { if (wt < t.nchunks) { strip = t.nstrips + x.left; r0 = wt * t.rows_per_chunk; r1 = min(g.ny, r0 + t.rows_per_chunk); found = true; } }
+    if (!found) return false;
+  }
+  // strip index -> first column: regular strips, then the left extra strip, then the right one
+  const int sx = strip < t.nstrips ? strip * TL_STRIP : ((x.left && strip == t.nstrips) ? -TL_STRIP : t.nstrips * TL_STRIP);
+  m.j0 = max(ylo, r0);
+  m.j1 = min(yhi, r1);
+  m.i0 = sx + 2 * m.lane;
+  m.acta = m.i0 >= xlo && m.i0 < xhi;
+  m.actb = m.i0 + 1 >= xlo && m.i0 + 1 < xhi;
+  m.ld_ok = m.i0 >= -TL_XPAD && m.i0 + 1 < g.pitch - TL_XPAD;   // the pair lies inside the padded row
+  m.ecol = (m.lane == 0) ? sx - 1 : sx + TL_STRIP;
+  m.has_edge = (m.lane == 0) ? (m.ecol >= -TL_XPAD) : (m.lane == 31 && m.ecol < g.pitch - TL_XPAD);
+  return m.j0 < m.j1 && sx < xhi && sx + TL_STRIP > xlo;
+}
 
 // ------------------------------------------------------------------------------------------
 // Jacobi iteration, one kernel (k_jacobi_fused_ring):  r .= u ; u = (u0 + sum k*r_nbr) / diag ;

@@ -446,6 +446,121 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(cons
   }
 }
 
+// PPCG inner step, matrix-powers variant for tiles (algorithm, buffer rotation and citations:
+// PpcgDkParams in tl_kernels_fused.cuh).  Same marching scheme and the same per-cell expressions
+// as k_ppcg_inner_ring; what differs is the window it covers (the tile extended towards its
+// neighbour tiles by the steps left in the group), where sd and r come from / go to, and that
+// only a group's last step pushes halos and takes part in the tile exchange.
+template <int S, int MINB>
+__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_dk(const PpcgDkParams P) {
+  tl_pdl_entry();
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  __shared__ double sm[32];
+  SolveState *st = P.st;
+  const int it = st->iter;
+  if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
+  const int pp = st->inner_pp, n = st->inner_steps, k = P.k;
+  const int grp = pp / k, q = pp - grp * k, G = (n + k - 1) / k;
+  const int L = min(k, n - grp * k);                 // steps in this group
+  const int e = L - 1 - q;                           // extension of this step's window
+  const bool group_end = (q == L - 1);
+  const bool last = (pp + 1 == n);
+  const int Lnext = last ? 0 : min(k, n - (grp + 1) * k);
+  const double alpha = P.alphas[pp], beta = P.betas[pp];
+  const double *__restrict__ sin = (q == 0) ? ((grp & 1) ? P.sin1 : P.sin0) : (((q - 1) & 1) ? P.wb : P.wa);
+  double *__restrict__ sout = group_end ? (((grp + 1) & 1) ? P.sin1 : P.sin0) : ((q & 1) ? P.wb : P.wa);
+  const double *rin = (q == 0) ? (((G - grp) & 1) ? P.rin1 : P.rin0) : P.rw;
+  double *rout = group_end ? (((G - grp - 1) & 1) ? P.rin1 : P.rin0) : P.rw;
+  const Push8 &push_s = ((grp + 1) & 1) ? P.push_sin1 : P.push_sin0;          // halo targets of sout at a group end
+  const Push8 &push_r = ((G - grp - 1) & 1) ? P.push_rin1 : P.push_rin0;      // ... of rout
+  const double *__restrict__ kx = P.kx;
+  const double *__restrict__ ky = P.ky;
+  double *__restrict__ u = P.u;
+  const Geo g = P.g;
+  const int pitch = g.pitch;
+  const bool physL = g.phys & TL_PHYS_LEFT, physR = g.phys & TL_PHYS_RIGHT;
+  const bool physB = g.phys & TL_PHYS_BOTTOM, physT = g.phys & TL_PHYS_TOP;
+  const int xlo = physL ? 0 : -e, xhi = g.nx + (physR ? 0 : e);
+  const int ylo = physB ? 0 : -e, yhi = g.ny + (physT ? 0 : e);
+
+  double acc[1] = {0.0};
+  MarchCtx m;
+  if (tl_march_setup_ext(g, P.t, P.ext, xlo, xhi, ylo, yhi, m)) {
+    const double2 z2 = make_double2(0.0, 0.0);
+    const bool ina = m.i0 >= 0 && m.i0 < g.nx, inb = m.i0 + 1 >= 0 && m.i0 + 1 < g.nx;   // interior cells
+    MarchCtx ml = m;                      // for the ring: the pointwise fields are loaded as pairs
+    ml.acta = m.acta || m.actb;
+    MarchCtx mi = m;                      // for the halo write-through: interior cells only
+    mi.acta = ina; mi.actb = ina && inb;
+    RingMarch<S> rg;
+    rg.init(ring_raw, m);
+    double2 Xm, Xc, kyc;
+    double XcE;
+    {
+      const int jm = (m.j0 == 0 && physB) ? 0 : m.j0 - 1;
+      const long om = (long)jm * pitch + m.i0, oc = (long)m.j0 * pitch + m.i0;
+      Xm = m.ld_ok ? tl_ld2(sin + om) : z2;
+      Xc = m.ld_ok ? tl_ld2(sin + oc) : z2;
+      kyc = m.ld_ok ? tl_ld2(ky + oc) : z2;
+      XcE = m.has_edge ? __ldg(sin + (long)m.j0 * pitch + m.ecol) : 0.0;
+    }
+#pragma unroll
+    for (int d = 0; d < S - 1; d++) {
+      if (m.j0 + d < m.j1) rg.issue(g, ml, physT, m.j0 + d, d, sin, ky, kx, rin, u);
+      tl_cp_commit();
+    }
+    for (int j = m.j0; j < m.j1; j++) {
+      if (j + S - 1 < m.j1) rg.issue(g, ml, physT, j + S - 1, rg.fill, sin, ky, kx, rin, u);
+      tl_cp_commit();
+      tl_cp_wait<S - 1>();
+      const RingRow cur = rg.take(ml, true, true);
+      const double2 Xn = cur.x;
+      double wa, wb;
+      tl_stencil2(g, m, physL, physR, Xm, Xc, Xn, XcE, cur.kx, cur.kxe, kyc, cur.ky, wa, wb);
+      const double2 rn = make_double2(cur.a.x - wa, cur.a.y - wb);
+      const double2 un = make_double2(cur.b.x + Xc.x, cur.b.y + Xc.y);
+      const double2 sn = make_double2(alpha * Xc.x + beta * rn.x, alpha * Xc.y + beta * rn.y);
+      const long oc = (long)j * pitch + m.i0;
+      const bool jin = j >= 0 && j < g.ny;
+      if (m.acta && m.actb) {
+        tl_st2(rout + oc, rn); tl_st2(sout + oc, sn);
+      } else if (m.acta) {
+        rout[oc] = rn.x; sout[oc] = sn.x;
+      } else if (m.actb) {
+        rout[oc + 1] = rn.y; sout[oc + 1] = sn.y;
+      }
+      if (jin) {                                    // u and the dot product live on the interior only
+        if (ina && inb) tl_st2(u + oc, un);
+        else if (ina) u[oc] = un.x;
+        else if (inb) u[oc + 1] = un.y;
+        if (last) {
+          if (ina) acc[0] += rn.x * rn.x;
+          if (inb) acc[0] += rn.y * rn.y;
+        }
+        // reflective sides: as k_ppcg_inner_ring (PPCG.jl:76 reflects the step's input)
+        tl_reflect_edges(sout, g, mi, j, oc, last ? Xc : sn);
+        if (group_end) {
+          if (last) tl_push_deep(P.push_rin0, g, 1, m.i0, ina, inb, j, rn);        // the next matvec reads r one cell deep
+          else {
+            tl_push_deep(push_s, g, Lnext, m.i0, ina, inb, j, sn);
+            if (Lnext > 1) tl_push_deep(push_r, g, Lnext - 1, m.i0, ina, inb, j, rn);
+          }
+        }
+      }
+      Xm = Xc; Xc = Xn; XcE = cur.xe; kyc = cur.ky;
+    }
+    tl_cp_wait<0>();
+  }
+  if (tl_kernel_tail(acc, last, st, P.partials, group_end ? P.cd : nullptr, sm)) {
+    if (last) {
+      st->red_rr_local = acc[0];      // PPCG.jl:88
+      st->red_rr = acc[0];
+      st->iter = it + 1;
+    }
+    st->inner_pp = pp + 1;
+  }
+}
+
 // Jacobi iteration (algorithm and citations: JacobiParams in tl_kernels_fused.cuh).
 template <int S, int MINB>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_jacobi_fused_ring(const JacobiParams P) {

@@ -28,7 +28,7 @@ class TeaLeafError(RuntimeError):
 class SolveInfo(C.Structure):
     """tl_solve_info"""
     _fields_ = [("iters", C.c_int), ("cg_iters", C.c_int), ("cheby_iters", C.c_int), ("est_iters", C.c_int),
-                ("inner_total", C.c_int), ("reserved", C.c_int), ("error", C.c_double), ("eigmin", C.c_double),
+                ("inner_total", C.c_int), ("halo_depth_k", C.c_int), ("error", C.c_double), ("eigmin", C.c_double),
                 ("eigmax", C.c_double), ("solve_ms", C.c_double), ("kernel_launches", C.c_longlong)]
 
     def as_dict(self):
@@ -81,7 +81,7 @@ SIGNATURES = {
     "tl_field_summary": (_I, [_P, _D, _DP, _DP, _DP, _DP]),
     "tl_cg_solve": (_I, [_P, _I, _D, _D, _D, _I, C.POINTER(SolveInfo), _DP, _DP]),
     "tl_cheby_solve": (_I, [_P, _I, _D, _D, _D, _I, _I, _D, _I, C.POINTER(SolveInfo)]),
-    "tl_ppcg_solve": (_I, [_P, _I, _D, _D, _D, _I, _I, _D, _I, _I, C.POINTER(SolveInfo)]),
+    "tl_ppcg_solve": (_I, [_P, _I, _D, _D, _D, _I, _I, _D, _I, _I, _I, C.POINTER(SolveInfo)]),
     "tl_jacobi_solve": (_I, [_P, _I, _D, _D, _D, _I, C.POINTER(SolveInfo)]),
     "tl_time_kernel": (_I, [_P, C.c_char_p, _I, _DP]),
     "tl_timer_start": (_I, [_P]),

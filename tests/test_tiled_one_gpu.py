@@ -92,3 +92,49 @@ def test_tiles_on_one_gpu_match_oracle(grid, solver, nx, ny, over):
 def test_two_timesteps_tiled():
     got = run_tiled((2, 2), "cg", 160, 160, steps=2)
     check_against_oracle(got, run_oracle("cg", 160, 160, steps=2), "cg")
+
+
+# ---- matrix-powers PPCG: one tile exchange per k inner steps -------------------------------
+DK_CASES = [
+    # grid, nx, ny, inner steps, halo_depth, k
+    ((1, 2), 192, 160, 6, 2, 2),
+    ((2, 1), 150, 96, 5, 2, 2),
+    ((2, 2), 131, 150, 5, 2, 2),
+    ((2, 2), 150, 131, 10, 4, 4),
+    ((2, 2), 129, 140, 7, 4, 3),
+    ((1, 4), 96, 256, 8, 3, 3),
+    ((4, 1), 300, 64, 4, 4, 4),
+    ((3, 3), 200, 190, 9, 5, 5),
+    ((2, 2), 128, 128, 3, 8, 8),      # k larger than the number of inner steps
+]
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("grid,nx,ny,inner,hd,k", DK_CASES,
+                         ids=[f"{g[0]}x{g[1]}-{nx}x{ny}-inner{n}-hd{hd}-k{k}" for g, nx, ny, n, hd, k in DK_CASES])
+def test_ppcg_depth_k_is_bit_identical_to_depth_1(grid, nx, ny, inner, hd, k):
+    """Grouping the inner steps (halo_depth_k = k) must not change a single bit relative to the
+    exchange-every-step schedule: the cells a tile computes in its halos are the owner's
+    arithmetic on the owner's inputs.  Both are also held against the oracle."""
+    over = {"ppcginnersteps": inner, "halodepth": hd}
+    fields = ("u", "energy", "r", "sd", "p")
+    base = run_tiled(grid, "ppcg", nx, ny, over={**over, "ppcghalodepth": 1}, fields=fields)
+    deep = run_tiled(grid, "ppcg", nx, ny, over={**over, "ppcghalodepth": k}, fields=fields)
+    assert [r["halo_depth_k"] for r in base[0]] == [1] and [r["halo_depth_k"] for r in deep[0]] == [min(k, inner)]
+    assert [r["iters"] for r in base[0]] == [r["iters"] for r in deep[0]]
+    assert [r["error"] for r in base[0]] == [r["error"] for r in deep[0]]
+    assert base[0][0]["inner_total"] > 0
+    for f in fields:
+        a, b = base[2][f][hd:-hd, hd:-hd], deep[2][f][hd:-hd, hd:-hd]
+        np.testing.assert_array_equal(a, b, err_msg=f)
+    assert base[1] == deep[1]
+    check_against_oracle(deep, run_oracle("ppcg", nx, ny, over=over), "ppcg", hd=hd)
+
+
+@pytest.mark.timeout(600)
+def test_ppcg_depth_k_two_timesteps_default_auto():
+    """halo_depth_k = 0 (automatic) picks halo_depth; state carried across timesteps."""
+    over = {"ppcginnersteps": 6, "halodepth": 3}
+    got = run_tiled((2, 2), "ppcg", 140, 120, steps=2, over=over)
+    assert [r["halo_depth_k"] for r in got[0]] == [3, 3]
+    check_against_oracle(got, run_oracle("ppcg", 140, 120, steps=2, over=over), "ppcg", hd=3)
