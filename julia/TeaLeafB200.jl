@@ -174,7 +174,8 @@ function solve!(chunk::B200Chunk, set::Settings, rx::Float64, ry::Float64)
     check(chunk, ccall((:tl_ppcg_solve, LIB), Cint,
                        (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Cint, Cint, Ref{SolveInfo}),
                        chunk.ctx, set.coefficient, rx, ry, set.eps, set.maxiters, set.presteps, set.epslim,
-                       set.errorswitch, set.ppcginnersteps, 0 #= halo_depth_k: automatic = set.halodepth =#, info))
+                       set.errorswitch, set.ppcginnersteps,
+                       hasproperty(set, :ppcghalodepth) ? set.ppcghalodepth : 0 #= halo_depth_k; 0: automatic = set.halodepth =#, info))
     resettoexchange!(set); set.toexchange[:p] = true
     chunk.eigmin, chunk.eigmax = info[].eigmin, info[].eigmax
     iters, error = info[].iters, info[].error

@@ -195,7 +195,7 @@ class DeviceChunk:
         info = _lib.SolveInfo()
         self._ck(self._l.tl_ppcg_solve(self.ctx, s.coefficient, rx, ry, s.eps, min(s.maxiters, self.maxiters),
                                        s.presteps, s.epslim, int(s.errorswitch), s.ppcginnersteps,
-                                       int(getattr(s, "ppcghalodepth", 0)), C.byref(info)))
+                                       int(s.ppcghalodepth), C.byref(info)))
         return info.as_dict()
 
     def jacobi_solve(self, s: Settings, rx: float, ry: float) -> dict:

@@ -9,8 +9,9 @@ Follows `src/settings.jl:39-78` (defaults), `:90-135` (`Settings(infile)`), `:14
 Appendix B, with two documented corrections from Appendix A:
   #6  the state-geometry nudge uses the final dx, dy (two-pass);
   #26 blank / comment lines in tea.problems are tolerated.
-And two extensions the north-star asks for: a leading `tl_` on any key is stripped and
-`use_chebyshev` is accepted as `use_cheby`.
+And three extensions the north-star asks for: a leading `tl_` on any key is stripped,
+`use_chebyshev` is accepted as `use_cheby`, and `ppcg_halo_depth=k` sets the depth of the tile
+exchange of the PPCG inner steps (matrix-powers groups; results do not depend on it).
 """
 from __future__ import annotations
 
@@ -78,6 +79,9 @@ class Settings:
     states: List[State] = field(default_factory=list)
     debugfile: str = ""
     problemfile: str = "tea.problems"
+    # extension (north_star "depth-k halos"): exchange depth of the PPCG inner steps between tiles,
+    # 0 = halo_depth.  Deck key `ppcg_halo_depth` / `tl_ppcg_halo_depth`; no effect on the result.
+    ppcghalodepth: int = 0
 
     def recompute_spacing(self) -> None:
         """src/settings.jl:132-133 (and Appendix A #23 for the -x/-y overrides)."""
@@ -96,7 +100,7 @@ def resettoexchange(s: Settings) -> None:
 _FIELD_TYPES = {f.name: f.type for f in dataclasses.fields(Settings)}
 _SETTABLE = {
     "endstep": int, "presteps": int, "maxiters": int, "coefficient": int, "ppcginnersteps": int,
-    "summaryfrequency": int, "halodepth": int, "xcells": int, "ycells": int,
+    "summaryfrequency": int, "halodepth": int, "xcells": int, "ycells": int, "ppcghalodepth": int,
     "errorswitch": bool, "checkresult": bool,
     "eps": float, "dtinit": float, "endtime": float, "epslim": float,
     "xmin": float, "ymin": float, "xmax": float, "ymax": float,

@@ -35,6 +35,7 @@ y_cells=20
 tl_max_iters=77
 tl_use_chebyshev
 tl_ppcg_inner_steps=4
+tl_ppcg_halo_depth=2
 test_problem 5
 unknown_key=3
 error_switch=true
@@ -48,6 +49,7 @@ end_step=1
     s = tl.parse_settings_text(text)
     assert s.xcells == 20 and s.maxiters == 77 and s.solver == "cheby" and s.ppcginnersteps == 4
     assert s.errorswitch is True and s.checkresult is False and s.coefficient == 2
+    assert s.ppcghalodepth == 2 and tl.Settings().ppcghalodepth == 0   # extension: depth-k tile exchange
     assert s.states[1].geometry == "circular" and s.states[1].radius == 2.5
     assert s.states[2].geometry == "point"
     s2 = tl.parse_settings_text("use_cg\nuse_jacobi\nuse_nonsense\n")

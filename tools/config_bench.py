@@ -5,6 +5,7 @@ multi-GPU data path (comm = fused | nccl).  Launch with torch.distributed.run fo
 
   python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/config_bench.py \
       --solver cheby --global 4096 --max-iters 2000 [--comm nccl] [--inner 10] [--tile 16384]
+      [--halo-depth 4 --ppcg-halo-depth 4]      (PPCG: one tile exchange per 4 inner steps)
 
 Prints one JSON line per (case, comm) on rank 0: global cell-iterations/s from the device time of
 the solve (CUDA events on the solve stream, max over ranks), per-kernel-launch average, and the
@@ -30,6 +31,9 @@ def main():
     ap.add_argument("--tile", type=int, default=0, help="cells per GPU per side (weak scaling)")
     ap.add_argument("--max-iters", type=int, default=1000)
     ap.add_argument("--inner", type=int, default=10)
+    ap.add_argument("--ppcg-halo-depth", type=int, default=0,
+                    help="PPCG: tile exchange every k inner steps (0 = halo_depth; 1 = every step)")
+    ap.add_argument("--halo-depth", type=int, default=2)
     ap.add_argument("--comm", default="fused,nccl")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--opt", action="append", default=[], help="tl_set_option name=value (repeatable)")
@@ -56,9 +60,10 @@ def main():
         nx, ny = args.tile * px, args.tile * py
     else:
         nx = ny = args.glob or 4096
-    over = {"maxiters": args.max_iters}
+    over = {"maxiters": args.max_iters, "halodepth": args.halo_depth}
     if args.solver == "ppcg":
         over["ppcginnersteps"] = args.inner
+        over["ppcghalodepth"] = args.ppcg_halo_depth
     s = classic_settings(nx, ny=ny, steps=1, solver=args.solver, **over)
     comms = args.comm.split(",") if world > 1 else ["single"]
     for comm in comms:
@@ -95,7 +100,7 @@ def main():
             print(json.dumps({
                 "solver": args.solver, "global_cells": [nx, ny], "n_gpus": world, "decomposition": f"{px}x{py}",
                 "comm": comm, "options": args.opt, "iters": best["iters"], "cg_iters": best["cg_iters"], "cheby_or_outer_iters": best["cheby_iters"],
-                "inner_steps_total": best["inner_total"], "error": best["error"], "solve_ms": ms,
+                "inner_steps_total": best["inner_total"], "halo_depth_k": best.get("halo_depth_k"), "error": best["error"], "solve_ms": ms,
                 "cell_iterations_per_s": cells * work_iters / (ms * 1e-3),
                 "us_per_sweep": 1e3 * ms / max(work_iters, 1),
                 "algorithmic_gbs_per_gpu": alg / (ms * 1e-3) / 1e9 / world,
