@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs, never by the product path.  PARITY UNPINNED against the
-reference itself (no Julia here, no golden vectors in the reference); see the C file header.
+reference itself (no Julia here, no golden vectors in the reference), pinned externally by
+upstream TeaLeaf's published QA checking values (tests/test_upstream_pin.py); see the C file header.
 
 `OracleChunk` exposes the same kernel names as tealeaf.jl_b200/device.py's DeviceChunk, so the
 host driver (app.diffuse, solvers.*.solve_stepwise) runs unchanged on either.
