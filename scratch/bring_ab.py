@@ -1,0 +1,28 @@
+# A/B: kernel B flavours (b_ring = 0 / 6 / 8) and the persistent CG kernel with the relaxed barrier
+import sys, os
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')
+import tealeaf_jl_b200 as tl
+from conftest import classic_settings
+from tealeaf_jl_b200.device import DeviceChunk
+for N in (4096, 8192, 2048, 1024, 256):
+    iters = 2000 if N <= 1024 else (600 if N <= 4096 else 300)
+    ref = None
+    for opts in ({"b_ring": 0}, {"b_ring": 6}, {"b_ring": 8}, {"b_ring": 0}, {"b_ring": 6}, {"b_ring": 8}, {"cg_persist": 1}, {"cg_persist": 1}):
+        s = classic_settings(N, steps=1, solver='cg', maxiters=iters)
+        chunk, geom = tl.initialiseapp(s, backend=DeviceChunk)
+        for k, v in opts.items():
+            chunk.set_option(k, v)
+        rx, ry = s.dtinit / s.dx ** 2, s.dtinit / s.dy ** 2
+        best = None
+        for _ in range(3):
+            chunk.copy_field("energy", "energy0")
+            tl.haloupdate(chunk, s, 1, ["energy", "density"])
+            info = chunk.cg_solve(s, rx, ry)
+            m_ = info['solve_ms'] / info['iters']
+            best = m_ if best is None else min(best, m_)
+        kb = min(chunk.time_kernel('cg_fused_r', 30) for _ in range(3))
+        sig = (info['iters'], info['error'])
+        ref = ref or sig
+        print(f"[bring] N={N} {opts}  us/iter={best * 1e3:.2f}  B alone={kb * 1e3:.2f} us ({24 * N * N / kb / 1e9:.2f} TB/s)  "
+              f"G cell-it/s={N * N / best / 1e6:.2f}  identical={sig == ref}", flush=True)
+        chunk.close()

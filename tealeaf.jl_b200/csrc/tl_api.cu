@@ -21,6 +21,7 @@
 #include "tl_kernels_basic.cuh"
 #include "tl_kernels_fused.cuh"
 #include "tl_kernels_ring.cuh"
+#include "tl_kernels_persist.cuh"
 #include "tl_eigen.h"
 
 #define TL_MAX_GRID 4096
@@ -113,6 +114,9 @@ struct tl_ctx {
   bool comm_ready = false;
   int use_pdl = 0;          // programmatic dependent launch between the kernels of the iteration loops: measured
                             // SLOWER (profiles/r01d_pdl_sweep.log: 1024^2 CG 24.7 -> 27.6 us/iteration), kept as an option
+  int b_ring = 0;           // kernel B flavour: 0 = register batches of 4 rows; 6 / 8 = cp.async ring of that depth (4 / 3 CTAs per SM)
+  int cg_persist = 0;       // 1: the CG loop of a single tile runs as ONE persistent cooperative kernel (tl_kernels_persist.cuh)
+  PersistSync *psync = nullptr;
   int comm_fused = 1;       // 1: halo pushes + mailbox allreduce inside the kernels; 0: halo-pull kernels + NCCL
   CommDev *d_comm = nullptr;   // device copy of the mailbox table (in the slab)
   MailSlot *mail = nullptr;
@@ -281,6 +285,8 @@ extern "C" int tl_abi_version(void) { return TL_ABI_VERSION; }
 extern "C" const char *tl_last_error(const tl_ctx *c) { return c ? c->err.c_str() : "null context"; }
 
 static std::string g_create_error;
+extern "C" int tl_set_option(tl_ctx *c, const char *name, double value);
+extern "C" void tl_destroy(tl_ctx *c);
 
 extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_depth, int max_iters, int device,
                               int rank, int px, int py) {
@@ -323,6 +329,7 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
   const size_t off_part = bytes; bytes += 4 * TL_MAX_GRID * sizeof(double);
   const size_t off_mail = bytes; bytes += 2 * TL_MAX_RANKS * sizeof(MailSlot);
   const size_t off_comm = bytes; bytes += (sizeof(CommDev) + 255) / 256 * 256;
+  const size_t off_psync = bytes; bytes += (sizeof(PersistSync) + 255) / 256 * 256;
   c->slab_bytes = bytes;
   cudaError_t e = cudaMalloc((void **)&c->slab, bytes);
   if (e != cudaSuccess) {
@@ -341,6 +348,7 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
   c->partials = (double *)(c->slab + off_part);
   c->mail = (MailSlot *)(c->slab + off_mail);
   c->d_comm = (CommDev *)(c->slab + off_comm);
+  c->psync = (PersistSync *)(c->slab + off_psync);
   if (cudaMallocHost((void **)&c->h_st, 2 * sizeof(SolveState)) != cudaSuccess ||
       cudaMallocHost((void **)&c->h_scal, 64 * sizeof(double)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -355,6 +363,26 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
   compute_tiling(c);
   cudaDeviceSynchronize();
   *out = c;
+  // default options for every context of the process: TEALEAF_B200_OPTS="name=value,name=value"
+  // (A/B runs of bench.py and the test-suite without code changes); unknown names are an error
+  if (const char *env = getenv("TEALEAF_B200_OPTS")) {
+    std::string all(env);
+    size_t pos = 0;
+    while (pos < all.size()) {
+      size_t end = all.find(',', pos);
+      if (end == std::string::npos) end = all.size();
+      const std::string kv = all.substr(pos, end - pos);
+      pos = end + 1;
+      const size_t eq = kv.find('=');
+      if (kv.empty()) continue;
+      if (eq == std::string::npos || tl_set_option(c, kv.substr(0, eq).c_str(), atof(kv.c_str() + eq + 1)) != TL_OK) {
+        g_create_error = "bad TEALEAF_B200_OPTS entry: " + kv;
+        tl_destroy(c);
+        *out = nullptr;
+        return TL_ERR_ARG;
+      }
+    }
+  }
   return TL_OK;
 }
 
@@ -400,6 +428,12 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "b_reverse") c->b_reverse = value != 0.0;
   else if (n == "comm_fused") c->comm_fused = value != 0.0;
   else if (n == "use_pdl") c->use_pdl = value != 0.0;
+  else if (n == "cg_persist") c->cg_persist = value != 0.0;
+  else if (n == "b_ring") {
+    const int d = (int)value;
+    if (d != 0 && d != 6 && d != 8) return tl_fail(c, TL_ERR_ARG, "b_ring must be 0, 6 or 8");
+    c->b_ring = d;
+  }
   else if (n == "ppcg_halo_depth") {   // exchange depth of the PPCG inner steps on tiles: 0 = auto (halo_depth)
     if (value < 0 || value > c->g.hd) return tl_fail(c, TL_ERR_ARG, "ppcg_halo_depth must be in 0..halo_depth");
     c->ppcg_depth_k = (int)value;
@@ -1018,6 +1052,27 @@ static int launch_ppcg_inner(tl_ctx *c) {
   return TL_OK;
 }
 
+// kernel B in the configured flavour
+template <int D, int MINB>
+static int launch_b_ring(tl_ctx *c, const CgBParams &P) {
+  const int smem = (TL_FUSED_THREADS / 32) * D * TL_BRING_ROW_BYTES;
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_cg_fused_r_ring<D, MINB>, smem, &prepared));
+  CU(c, tl_launch(c, k_cg_fused_r_ring<D, MINB>, c->pw_grid, TL_FUSED_THREADS, smem, P));
+  return TL_OK;
+}
+static int launch_cg_b(tl_ctx *c) {
+  const CgBParams P = cg_b_params(c);
+  switch (c->b_ring) {
+    case 0: CU(c, tl_launch(c, k_cg_fused_r, c->pw_grid, TL_FUSED_THREADS, 0, P)); break;
+    case 6: TRY((launch_b_ring<6, 4>(c, P))); break;
+    case 8: TRY((launch_b_ring<8, 3>(c, P))); break;
+    default: return tl_fail(c, TL_ERR_STATE, "internal: b_ring %d", c->b_ring);
+  }
+  CHECK_LAUNCH(c);
+  return TL_OK;
+}
+
 // One CG iteration on the stream: kernel A, kernel B.  Tiled (fused mode): the same two kernels --
 // they push their edge cells into the neighbours' halos and sum pw / rr over the tiles in their
 // tails.  Legacy mode (comm_fused = 0, kept for A/B measurements): halo-pull kernels and NCCL.
@@ -1031,7 +1086,7 @@ static int enqueue_cg_iteration(tl_ctx *c) {
   }
   TRY(launch_cg_a<true>(c));
   if (legacy) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
-  CU(c, tl_launch(c, k_cg_fused_r, c->pw_grid, TL_FUSED_THREADS, 0, cg_b_params(c)));
+  TRY(launch_cg_b(c));
   if (legacy) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
   c->launches += 2;
   return TL_OK;
@@ -1101,7 +1156,52 @@ static int solve_preamble(tl_ctx *c, int coef, double rx, double ry, const StopC
   return TL_OK;
 }
 
+// The CG loop as one persistent cooperative kernel (single tile; option cg_persist).
+template <int S, int MINB>
+static int launch_cg_persist(tl_ctx *c, const CgPersistParams &P0) {
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_cg_persist<S, MINB>, smem, &prepared));
+  int per_sm = 0;
+  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persist<S, MINB>, TL_FUSED_THREADS, smem));
+  if (per_sm < 1) return tl_fail(c, TL_ERR_STATE, "persistent CG kernel does not fit on an SM");
+  CgPersistParams P = P0;
+  const int grid = std::max(1, std::min(per_sm * c->num_sms, std::max(P.nitems_a, P.nitems_b)));
+  CU(c, cudaMemsetAsync(c->psync, 0, sizeof(PersistSync), c->stream));
+  void *args[] = {(void *)&P};
+  CU(c, cudaLaunchCooperativeKernel((const void *)k_cg_persist<S, MINB>, dim3((unsigned)grid), dim3(TL_FUSED_THREADS), args,
+                                    (size_t)smem, c->stream));
+  return TL_OK;
+}
+
+static int cg_phase_persist(tl_ctx *c, SolveState *fin) {
+  CgPersistParams P;
+  P.A = cg_a_params(c);
+  P.B = cg_b_params(c);
+  P.sync = c->psync;
+  P.part_a = c->partials;
+  P.part_b = c->partials + TL_MAX_GRID;
+  P.nitems_a = c->fused_grid;
+  P.nitems_b = c->pw_grid;
+  switch (c->ring_eff) {
+    case 3: TRY((launch_cg_persist<3, 3>(c, P))); break;
+    case 4: TRY((launch_cg_persist<4, 2>(c, P))); break;
+    default: return tl_fail(c, TL_ERR_STATE, "cg_persist needs ring depth 3 or 4 (is %d)", c->ring_eff);
+  }
+  c->launches += 1;
+  int aborted = 0;
+  CU(c, cudaMemcpyAsync(&c->h_st[0], c->st, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(&aborted, &c->psync->abort, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  *fin = c->h_st[0];
+  if (aborted) return tl_fail(c, TL_ERR_STATE, "persistent CG kernel: grid barrier timed out");
+  if (!tl_should_stop(fin->iter, fin->red_rr, fin->cfg))
+    return tl_fail(c, TL_ERR_STATE, "internal: persistent CG kernel ended before the stop rule fired");
+  return TL_OK;
+}
+
 static int cg_phase(tl_ctx *c, SolveState *fin) {
+  if (c->cg_persist && c->nranks == 1) return cg_phase_persist(c, fin);
   auto enq = [&]() { return enqueue_cg_iteration(c); };
   auto stop = [&](const SolveState &s) { return tl_should_stop(s.iter, s.red_rr, s.cfg); };
   return run_chunks(c, &c->g_cg, &c->g_cg_iters, c->graph_iters, 2, enq, stop, fin);
@@ -1600,7 +1700,7 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
   auto launch = [&]() -> int {
     if (k == "cg_fused_w") TRY(launch_cg_a<true>(c));
     else if (k == "cg_fused_w_nou") TRY(launch_cg_a<false>(c));
-    else if (k == "cg_fused_r") CU(c, tl_launch(c, k_cg_fused_r, c->pw_grid, TL_FUSED_THREADS, 0, cg_b_params(c)));
+    else if (k == "cg_fused_r") TRY(launch_cg_b(c));
     else if (k == "cheby_fused") TRY(launch_cheby<false>(c));
     else if (k == "ppcg_inner") TRY(launch_ppcg_inner(c));
     else return tl_fail(c, TL_ERR_ARG, "tl_time_kernel: unknown kernel %s", kernel);

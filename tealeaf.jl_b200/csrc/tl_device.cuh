@@ -270,6 +270,24 @@ __device__ __forceinline__ bool tl_kernel_tail(double (&acc)[1], bool do_sum, So
 }
 
 __device__ __forceinline__ double2 tl_ld2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+// Coherent variants for data that other CTAs rewrite INSIDE the same launch (persistent kernels):
+// ld.global.cg reads through L2 and never uses the non-coherent (read-only) path.
+__device__ __forceinline__ double2 tl_ld2_cg(const double *p) {
+  double2 v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double tl_ld1_cg(const double *p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+template <bool COH>
+__device__ __forceinline__ double tl_ld1(const double *p) { return COH ? tl_ld1_cg(p) : *p; }
+template <bool COH>
+__device__ __forceinline__ double tl_ldg1(const double *p) { return COH ? tl_ld1_cg(p) : __ldg(p); }
+template <bool COH>
+__device__ __forceinline__ double2 tl_ldg2(const double *p) { return COH ? tl_ld2_cg(p) : tl_ld2(p); }
 __device__ __forceinline__ double2 tl_ld2_rw(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void tl_st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 

@@ -28,9 +28,11 @@ struct MarchCtx {
   bool acta, actb, ld_ok, has_edge;
 };
 
-__device__ __forceinline__ bool tl_march_setup(const Geo &g, const Tiling &t, MarchCtx &m, int reverse = 0) {
+// `blk` = the work item: 8 consecutive warp tasks (a CTA of the multi-wave kernels, or an item a
+// persistent CTA fetched from the queue, tl_kernels_persist.cuh)
+__device__ __forceinline__ bool tl_march_setup_blk(const Geo &g, const Tiling &t, MarchCtx &m, int blk, int reverse) {
   m.lane = threadIdx.x & 31;
-  int wt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int wt = blk * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wt >= t.nstrips * t.nchunks) return false;
   if (reverse) wt = t.nstrips * t.nchunks - 1 - wt;
   const int s = wt % t.nstrips, q = wt / t.nstrips;
@@ -43,6 +45,9 @@ __device__ __forceinline__ bool tl_march_setup(const Geo &g, const Tiling &t, Ma
   m.ecol = (m.lane == 0) ? s * TL_STRIP - 1 : s * TL_STRIP + TL_STRIP;
   m.has_edge = (m.lane == 0) || (m.lane == 31 && m.ecol <= g.nx);
   return m.j0 < m.j1;
+}
+__device__ __forceinline__ bool tl_march_setup(const Geo &g, const Tiling &t, MarchCtx &m, int reverse = 0) {
+  return tl_march_setup_blk(g, t, m, blockIdx.x, reverse);
 }
 
 // Stores this lane's cells (i0, i0+1) of row j into the neighbours' depth-1 halo cells when they
@@ -150,6 +155,48 @@ struct CgBParams {
   Push push_r;
 };
 
+// The rows of one work item of kernel B.  COH = true (persistent kernel: r and w change inside the
+// launch) keeps every load coherent (no ld.global.nc).
+template <bool COH>
+__device__ __forceinline__ void tl_cg_b_item(const CgBParams &P, double alpha, int blk, double &acc0) {
+  const Geo g = P.g;
+  double *__restrict__ r = P.r;
+  const double *w = P.w;
+  const unsigned long long pol_r = tl_policy(P.hint_keep), pol_w = tl_policy(P.hint_stream);
+  const bool tiled = P.cd != nullptr;
+  MarchCtx m;
+  if (!tl_march_setup_blk(g, P.t, m, blk, P.reverse)) return;
+  int j = m.j0;
+  if (m.actb) {
+    for (; j + 4 <= m.j1; j += 4) {
+      double2 rv[4], wv[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const long o = (long)(j + q) * g.pitch + m.i0;
+        rv[q] = COH ? tl_ld2_cg(r + o) : tl_ld2_hint(r + o, pol_r);
+        wv[q] = COH ? tl_ld2_cg(w + o) : tl_ld2_hint(w + o, pol_w);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const long o = (long)(j + q) * g.pitch + m.i0;
+        rv[q].x = rv[q].x - alpha * wv[q].x;
+        rv[q].y = rv[q].y - alpha * wv[q].y;
+        tl_st2_hint(r + o, rv[q], pol_r);
+        acc0 += rv[q].x * rv[q].x;
+        acc0 += rv[q].y * rv[q].y;
+        if (tiled) tl_push_edges(P.push_r, g, m, j + q, rv[q]);
+      }
+    }
+  }
+  for (; j < m.j1; j++) {
+    const long o = (long)j * g.pitch + m.i0;
+    double2 v = make_double2(0.0, 0.0);
+    if (m.acta) { v.x = tl_ld1<COH>(r + o) - alpha * tl_ld1<COH>(w + o); r[o] = v.x; acc0 += v.x * v.x; }
+    if (m.actb) { v.y = tl_ld1<COH>(r + o + 1) - alpha * tl_ld1<COH>(w + o + 1); r[o + 1] = v.y; acc0 += v.y * v.y; }
+    if (tiled) tl_push_edges(P.push_r, g, m, j, v);
+  }
+}
+
 __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBParams P) {
   tl_pdl_entry();
   __shared__ double sm[32];
@@ -160,47 +207,11 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBPar
   const double pw = st->red_pw;
   const double alpha = rr_cur / pw;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_pw[it + 1] = pw;
-  const Geo g = P.g;
-  double *__restrict__ r = P.r;
-  const double *__restrict__ w = P.w;
-  const unsigned long long pol_r = tl_policy(P.hint_keep), pol_w = tl_policy(P.hint_stream);
-  const bool tiled = P.cd != nullptr;
   double acc[1] = {0.0};
-  MarchCtx m;
-  if (tl_march_setup(g, P.t, m, P.reverse)) {
-    int j = m.j0;
-    if (m.actb) {
-      for (; j + 4 <= m.j1; j += 4) {
-        double2 rv[4], wv[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const long o = (long)(j + q) * g.pitch + m.i0;
-          rv[q] = tl_ld2_hint(r + o, pol_r);
-          wv[q] = tl_ld2_hint(w + o, pol_w);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const long o = (long)(j + q) * g.pitch + m.i0;
-          rv[q].x = rv[q].x - alpha * wv[q].x;
-          rv[q].y = rv[q].y - alpha * wv[q].y;
-          tl_st2_hint(r + o, rv[q], pol_r);
-          acc[0] += rv[q].x * rv[q].x;
-          acc[0] += rv[q].y * rv[q].y;
-          if (tiled) tl_push_edges(P.push_r, g, m, j + q, rv[q]);
-        }
-      }
-    }
-    for (; j < m.j1; j++) {
-      const long o = (long)j * g.pitch + m.i0;
-      double2 v = make_double2(0.0, 0.0);
-      if (m.acta) { v.x = r[o] - alpha * w[o]; r[o] = v.x; acc[0] += v.x * v.x; }
-      if (m.actb) { v.y = r[o + 1] - alpha * w[o + 1]; r[o + 1] = v.y; acc[0] += v.y * v.y; }
-      if (tiled) tl_push_edges(P.push_r, g, m, j, v);
-    }
-  }
+  tl_cg_b_item<false>(P, alpha, blockIdx.x, acc[0]);
   if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
     st->red_rr_local = acc[0];
-    if (P.single || tiled) st->red_rr = acc[0];
+    if (P.single || P.cd != nullptr) st->red_rr = acc[0];
     st->iter = it + 1;
   }
 }

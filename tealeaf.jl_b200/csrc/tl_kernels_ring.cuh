@@ -42,23 +42,21 @@ __device__ __forceinline__ double tl_lds1(unsigned a) {
 }
 
 // CG kernel A (algorithm and citations: CgAParams in tl_kernels_fused.cuh).
-template <bool UPDATE_U, int S, int MINB>
-__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(const CgAParams P) {
-  tl_pdl_entry();
-  extern __shared__ __align__(128) unsigned char ring_raw[];
-  __shared__ double sm[32];
-  SolveState *st = P.st;
-  const int it = st->iter;
-  const double rr_cur = st->red_rr;
-  if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
-  const bool first = (it == st->cfg.first_it);
-  double beta = 0.0, alpha_prev = 0.0;
-  if (!first) {
-    const double rr_prev = P.hist_rr[it - 1];
-    beta = rr_cur / rr_prev;
-    alpha_prev = rr_prev / P.hist_pw[it];
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_rr[it] = rr_cur;
+// Scalars of the iteration a work item belongs to.
+struct CgAIter {
+  int it;
+  bool first;
+  double beta, alpha_prev;
+};
+
+// The rows of one work item (8 warp tasks) of kernel A.  COH = true (persistent kernel: r, p, u change
+// inside the launch) keeps the prologue loads coherent; the ring loads are cp.async (L2) either way.
+template <bool UPDATE_U, int S, bool COH>
+__device__ __forceinline__ void tl_cg_a_item(const CgAParams &P, const CgAIter &I, int blk, unsigned char *ring_raw,
+                                             double &acc0) {
+  const int it = I.it;
+  const bool first = I.first;
+  const double beta = I.beta, alpha_prev = I.alpha_prev;
   const double *__restrict__ pin = (it & 1) ? P.p1 : P.p0;
   double *__restrict__ pout = (it & 1) ? P.p0 : P.p1;
   const double *__restrict__ r = P.r;
@@ -74,114 +72,214 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
   const unsigned long long pol_keep = tl_policy(P.hint_keep), pol_stream = tl_policy(P.hint_stream);
   const bool tiled = P.cd != nullptr;
   const Push &push = (it & 1) ? P.push_p0 : P.push_p1;   // halo targets of pout
-  double acc[1] = {0.0};
   MarchCtx m;
-  if (tl_march_setup(g, P.t, m)) {
-    const double2 z2 = make_double2(0.0, 0.0);
-    auto comb = [&](double rv, double pv) { return first ? pv : beta * pv + rv; };
-    auto comb2 = [&](double2 rv, double2 pv) { return make_double2(comb(rv.x, pv.x), comb(rv.y, pv.y)); };
-    // this warp's ring; slot layout: [field 0..4][lane] double2, then 8 edge doubles
-    const unsigned ring = tl_smem_u32(ring_raw) + (threadIdx.x >> 5) * (S * TL_RING_STAGE_BYTES);
-    const unsigned lane_off = m.lane * 16;
-    const unsigned edge_off = TL_RING_FIELDS * 512 + (m.lane == 0 ? 0 : 24);   // lane 0: 3 doubles, lane 31: 3 doubles
-    auto issue = [&](int j, int stage) {
-      const unsigned base = ring + stage * TL_RING_STAGE_BYTES;
-      const int jn = (j + 1 >= g.ny && physT) ? g.ny - 1 : j + 1;
-      const long on = (long)jn * pitch + m.i0, oc = (long)j * pitch + m.i0;
-      if (m.ld_ok) {
-        tl_cp16_hint(base + 0 * 512 + lane_off, r + on, pol_keep);
-        tl_cp16_hint(base + 1 * 512 + lane_off, pin + on, pol_stream);
-        tl_cp16_hint(base + 2 * 512 + lane_off, ky + oc + pitch, pol_stream);
-        tl_cp16_hint(base + 3 * 512 + lane_off, kx + oc, pol_stream);
-      }
-      if (UPDATE_U && m.acta) tl_cp16_hint(base + 4 * 512 + lane_off, u + oc, pol_stream);
-      if (m.has_edge) {
-        const long oe = (long)jn * pitch + m.ecol;
-        tl_cp8(base + edge_off + 0, r + oe);
-        tl_cp8(base + edge_off + 8, pin + oe);
-        if (m.lane == 31) tl_cp8(base + edge_off + 16, kx + (long)j * pitch + m.ecol);
-      }
-    };
-    // prologue: rows j0-1 (clamped on a physical bottom) and j0, plain loads
-    double2 Xm, Xc, pc, kyc;
-    double XcE;
-    {
-      const int jm = (m.j0 == 0 && physB) ? 0 : m.j0 - 1;
-      const long om = (long)jm * pitch + m.i0, oc = (long)m.j0 * pitch + m.i0;
-      const double2 rm = m.ld_ok ? tl_ld2(r + om) : z2, pm = m.ld_ok ? tl_ld2(pin + om) : z2;
-      const double2 rc = m.ld_ok ? tl_ld2(r + oc) : z2;
-      pc = m.ld_ok ? tl_ld2(pin + oc) : z2;
-      kyc = m.ld_ok ? tl_ld2(ky + oc) : z2;
-      const long oe = (long)m.j0 * pitch + m.ecol;
-      const double re = m.has_edge ? __ldg(r + oe) : 0.0, pe = m.has_edge ? __ldg(pin + oe) : 0.0;
-      Xm = comb2(rm, pm);
-      Xc = comb2(rc, pc);
-      XcE = comb(re, pe);
+  if (!tl_march_setup_blk(g, P.t, m, blk, 0)) return;
+  const double2 z2 = make_double2(0.0, 0.0);
+  auto comb = [&](double rv, double pv) { return first ? pv : beta * pv + rv; };
+  auto comb2 = [&](double2 rv, double2 pv) { return make_double2(comb(rv.x, pv.x), comb(rv.y, pv.y)); };
+  // this warp's ring; slot layout: [field 0..4][lane] double2, then 8 edge doubles
+  const unsigned ring = tl_smem_u32(ring_raw) + (threadIdx.x >> 5) * (S * TL_RING_STAGE_BYTES);
+  const unsigned lane_off = m.lane * 16;
+  const unsigned edge_off = TL_RING_FIELDS * 512 + (m.lane == 0 ? 0 : 24);   // lane 0: 3 doubles, lane 31: 3 doubles
+  auto issue = [&](int j, int stage) {
+    const unsigned base = ring + stage * TL_RING_STAGE_BYTES;
+    const int jn = (j + 1 >= g.ny && physT) ? g.ny - 1 : j + 1;
+    const long on = (long)jn * pitch + m.i0, oc = (long)j * pitch + m.i0;
+    if (m.ld_ok) {
+      tl_cp16_hint(base + 0 * 512 + lane_off, r + on, pol_keep);
+      tl_cp16_hint(base + 1 * 512 + lane_off, pin + on, pol_stream);
+      tl_cp16_hint(base + 2 * 512 + lane_off, ky + oc + pitch, pol_stream);
+      tl_cp16_hint(base + 3 * 512 + lane_off, kx + oc, pol_stream);
     }
+    if (UPDATE_U && m.acta) tl_cp16_hint(base + 4 * 512 + lane_off, u + oc, pol_stream);
+    if (m.has_edge) {
+      const long oe = (long)jn * pitch + m.ecol;
+      tl_cp8(base + edge_off + 0, r + oe);
+      tl_cp8(base + edge_off + 8, pin + oe);
+      if (m.lane == 31) tl_cp8(base + edge_off + 16, kx + (long)j * pitch + m.ecol);
+    }
+  };
+  // prologue: rows j0-1 (clamped on a physical bottom) and j0, plain loads
+  double2 Xm, Xc, pc, kyc;
+  double XcE;
+  {
+    const int jm = (m.j0 == 0 && physB) ? 0 : m.j0 - 1;
+    const long om = (long)jm * pitch + m.i0, oc = (long)m.j0 * pitch + m.i0;
+    const double2 rm = m.ld_ok ? tl_ldg2<COH>(r + om) : z2, pm = m.ld_ok ? tl_ldg2<COH>(pin + om) : z2;
+    const double2 rc = m.ld_ok ? tl_ldg2<COH>(r + oc) : z2;
+    pc = m.ld_ok ? tl_ldg2<COH>(pin + oc) : z2;
+    kyc = m.ld_ok ? tl_ld2(ky + oc) : z2;
+    const long oe = (long)m.j0 * pitch + m.ecol;
+    const double re = m.has_edge ? tl_ldg1<COH>(r + oe) : 0.0, pe = m.has_edge ? tl_ldg1<COH>(pin + oe) : 0.0;
+    Xm = comb2(rm, pm);
+    Xc = comb2(rc, pc);
+    XcE = comb(re, pe);
+  }
 #pragma unroll
-    for (int d = 0; d < S - 1; d++) {
+  for (int d = 0; d < S - 1; d++) {
+    if (m.j0 + d < m.j1) issue(m.j0 + d, d);
+    tl_cp_commit();
+  }
+  int stage = 0;            // slot holding row j
+  int fill = S - 1;         // slot that receives row j + S - 1
+  for (int j = m.j0; j < m.j1; j++) {
+    if (j + S - 1 < m.j1) issue(j + S - 1, fill);
+    tl_cp_commit();
+    tl_cp_wait<S - 1>();
+    const unsigned base = ring + stage * TL_RING_STAGE_BYTES;
+    const double2 c_r = m.ld_ok ? tl_lds2(base + 0 * 512 + lane_off) : z2;
+    const double2 c_p = m.ld_ok ? tl_lds2(base + 1 * 512 + lane_off) : z2;
+    const double2 c_ky = m.ld_ok ? tl_lds2(base + 2 * 512 + lane_off) : z2;
+    const double2 c_kx = m.ld_ok ? tl_lds2(base + 3 * 512 + lane_off) : z2;
+    const double2 c_u = (UPDATE_U && m.acta) ? tl_lds2(base + 4 * 512 + lane_off) : z2;
+    const double c_re = m.has_edge ? tl_lds1(base + edge_off + 0) : 0.0;
+    const double c_pe = m.has_edge ? tl_lds1(base + edge_off + 8) : 0.0;
+    const double c_kxe = (m.lane == 31 && m.has_edge) ? tl_lds1(base + edge_off + 16) : 0.0;
+    stage = (stage + 1 == S) ? 0 : stage + 1;
+    fill = (fill + 1 == S) ? 0 : fill + 1;
+
+    const double2 Xn = comb2(c_r, c_p);
+    const double XnE = comb(c_re, c_pe);
+    double xl = __shfl_up_sync(0xffffffffu, Xc.y, 1);
+    double xr = __shfl_down_sync(0xffffffffu, Xc.x, 1);
+    double kxr = __shfl_down_sync(0xffffffffu, c_kx.x, 1);
+    if (m.lane == 0) xl = XcE;
+    if (m.lane == 31) { xr = XcE; kxr = c_kxe; }
+    const double La = (physL && m.i0 == 0) ? Xc.x : xl;
+    const double Ra = (physR && m.i0 == g.nx - 1) ? Xc.x : Xc.y;
+    const double Lb = Xc.x;
+    const double Rb = (physR && m.i0 + 1 == g.nx - 1) ? Xc.y : xr;
+    const double wa = ((((1.0 + c_kx.y) + c_kx.x) + c_ky.x) + kyc.x) * Xc.x -
+                      (c_kx.y * Ra + c_kx.x * La) - (c_ky.x * Xn.x + kyc.x * Xm.x);
+    const double wb = ((((1.0 + kxr) + c_kx.y) + c_ky.y) + kyc.y) * Xc.y -
+                      (kxr * Rb + c_kx.y * Lb) - (c_ky.y * Xn.y + kyc.y * Xm.y);
+    const long oc = (long)j * pitch + m.i0;
+    double2 un = z2;
+    if (UPDATE_U) un = make_double2(c_u.x + alpha_prev * pc.x, c_u.y + alpha_prev * pc.y);
+    if (m.actb) {
+      tl_st2_hint(w + oc, make_double2(wa, wb), pol_keep);
+      tl_st2_hint(pout + oc, Xc, pol_stream);
+      if (UPDATE_U) tl_st2_hint(u + oc, un, pol_stream);
+      acc0 += wa * Xc.x;
+      acc0 += wb * Xc.y;
+    } else if (m.acta) {
+      w[oc] = wa; pout[oc] = Xc.x;
+      if (UPDATE_U) u[oc] = un.x;
+      acc0 += wa * Xc.x;
+    }
+    // haloupdate!(.., [:u,:p]) CG.jl:22: reflective sides as a write-through, tile-internal
+    // sides as a push of p into the neighbour's halo (u's internal halos are filled after the loop)
+    tl_reflect_edges(pout, g, m, j, oc, Xc);
+    if (UPDATE_U) tl_reflect_edges(u, g, m, j, oc, un);
+    if (tiled) tl_push_edges(push, g, m, j, Xc);
+    Xm = Xc; Xc = Xn; XcE = XnE; pc = c_p; kyc = c_ky;
+  }
+  tl_cp_wait<0>();
+}
+
+template <bool UPDATE_U, int S, int MINB>
+__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(const CgAParams P) {
+  tl_pdl_entry();
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  __shared__ double sm[32];
+  SolveState *st = P.st;
+  const int it = st->iter;
+  const double rr_cur = st->red_rr;
+  if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
+  CgAIter I;
+  I.it = it;
+  I.first = (it == st->cfg.first_it);
+  I.beta = 0.0; I.alpha_prev = 0.0;
+  if (!I.first) {
+    const double rr_prev = P.hist_rr[it - 1];
+    I.beta = rr_cur / rr_prev;
+    I.alpha_prev = rr_prev / P.hist_pw[it];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_rr[it] = rr_cur;
+  double acc[1] = {0.0};
+  tl_cg_a_item<UPDATE_U, S, false>(P, I, blockIdx.x, ring_raw, acc[0]);
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
+    st->red_pw_local = acc[0];
+    if (P.single || P.cd != nullptr) st->red_pw = acc[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CG kernel B with the cp.async ring (k_cg_fused_r_ring): the same rows, the same arithmetic and
+// the same summation order as tl_cg_b_item, but the next D-1 rows of r and w are always in flight
+// as asynchronous copies into this warp's private ring (1 KB per row: r at +0, w at +512), instead
+// of batches of 4 rows loaded into registers -- the kernel is pure streaming, so bytes in flight
+// are its only lever.  Lanes read back only the bytes they copied themselves: no barriers.
+// ------------------------------------------------------------------------------------------
+#define TL_BRING_ROW_BYTES 1024
+template <int D, bool COH>
+__device__ __forceinline__ void tl_cg_b_item_ring(const CgBParams &P, double alpha, int blk, unsigned char *ring_raw,
+                                                  double &acc0) {
+  const Geo g = P.g;
+  double *r = P.r;
+  const double *w = P.w;
+  const unsigned long long pol_r = tl_policy(P.hint_keep), pol_w = tl_policy(P.hint_stream);
+  const bool tiled = P.cd != nullptr;
+  MarchCtx m;
+  if (!tl_march_setup_blk(g, P.t, m, blk, P.reverse)) return;
+  if (m.actb) {
+    const unsigned ring = tl_smem_u32(ring_raw) + (threadIdx.x >> 5) * (D * TL_BRING_ROW_BYTES) + m.lane * 16;
+    auto issue = [&](int j, int slot) {
+      const long o = (long)j * g.pitch + m.i0;
+      tl_cp16_hint(ring + slot * TL_BRING_ROW_BYTES, r + o, pol_r);
+      tl_cp16_hint(ring + slot * TL_BRING_ROW_BYTES + 512, w + o, pol_w);
+    };
+#pragma unroll
+    for (int d = 0; d < D - 1; d++) {
       if (m.j0 + d < m.j1) issue(m.j0 + d, d);
       tl_cp_commit();
     }
-    int stage = 0;            // slot holding row j
-    int fill = S - 1;         // slot that receives row j + S - 1
+    int stage = 0, fill = D - 1;
     for (int j = m.j0; j < m.j1; j++) {
-      if (j + S - 1 < m.j1) issue(j + S - 1, fill);
+      if (j + D - 1 < m.j1) issue(j + D - 1, fill);
       tl_cp_commit();
-      tl_cp_wait<S - 1>();
-      const unsigned base = ring + stage * TL_RING_STAGE_BYTES;
-      const double2 c_r = m.ld_ok ? tl_lds2(base + 0 * 512 + lane_off) : z2;
-      const double2 c_p = m.ld_ok ? tl_lds2(base + 1 * 512 + lane_off) : z2;
-      const double2 c_ky = m.ld_ok ? tl_lds2(base + 2 * 512 + lane_off) : z2;
-      const double2 c_kx = m.ld_ok ? tl_lds2(base + 3 * 512 + lane_off) : z2;
-      const double2 c_u = (UPDATE_U && m.acta) ? tl_lds2(base + 4 * 512 + lane_off) : z2;
-      const double c_re = m.has_edge ? tl_lds1(base + edge_off + 0) : 0.0;
-      const double c_pe = m.has_edge ? tl_lds1(base + edge_off + 8) : 0.0;
-      const double c_kxe = (m.lane == 31 && m.has_edge) ? tl_lds1(base + edge_off + 16) : 0.0;
-      stage = (stage + 1 == S) ? 0 : stage + 1;
-      fill = (fill + 1 == S) ? 0 : fill + 1;
-
-      const double2 Xn = comb2(c_r, c_p);
-      const double XnE = comb(c_re, c_pe);
-      double xl = __shfl_up_sync(0xffffffffu, Xc.y, 1);
-      double xr = __shfl_down_sync(0xffffffffu, Xc.x, 1);
-      double kxr = __shfl_down_sync(0xffffffffu, c_kx.x, 1);
-      if (m.lane == 0) xl = XcE;
-      if (m.lane == 31) { xr = XcE; kxr = c_kxe; }
-      const double La = (physL && m.i0 == 0) ? Xc.x : xl;
-      const double Ra = (physR && m.i0 == g.nx - 1) ? Xc.x : Xc.y;
-      const double Lb = Xc.x;
-      const double Rb = (physR && m.i0 + 1 == g.nx - 1) ? Xc.y : xr;
-      const double wa = ((((1.0 + c_kx.y) + c_kx.x) + c_ky.x) + kyc.x) * Xc.x -
-                        (c_kx.y * Ra + c_kx.x * La) - (c_ky.x * Xn.x + kyc.x * Xm.x);
-      const double wb = ((((1.0 + kxr) + c_kx.y) + c_ky.y) + kyc.y) * Xc.y -
-                        (kxr * Rb + c_kx.y * Lb) - (c_ky.y * Xn.y + kyc.y * Xm.y);
-      const long oc = (long)j * pitch + m.i0;
-      double2 un = z2;
-      if (UPDATE_U) un = make_double2(c_u.x + alpha_prev * pc.x, c_u.y + alpha_prev * pc.y);
-      if (m.actb) {
-        tl_st2_hint(w + oc, make_double2(wa, wb), pol_keep);
-        tl_st2_hint(pout + oc, Xc, pol_stream);
-        if (UPDATE_U) tl_st2_hint(u + oc, un, pol_stream);
-        acc[0] += wa * Xc.x;
-        acc[0] += wb * Xc.y;
-      } else if (m.acta) {
-        w[oc] = wa; pout[oc] = Xc.x;
-        if (UPDATE_U) u[oc] = un.x;
-        acc[0] += wa * Xc.x;
-      }
-      // haloupdate!(.., [:u,:p]) CG.jl:22: reflective sides as a write-through, tile-internal
-      // sides as a push of p into the neighbour's halo (u's internal halos are filled after the loop)
-      tl_reflect_edges(pout, g, m, j, oc, Xc);
-      if (UPDATE_U) tl_reflect_edges(u, g, m, j, oc, un);
-      if (tiled) tl_push_edges(push, g, m, j, Xc);
-      Xm = Xc; Xc = Xn; XcE = XnE; pc = c_p; kyc = c_ky;
+      tl_cp_wait<D - 1>();
+      double2 rv = tl_lds2(ring + stage * TL_BRING_ROW_BYTES);
+      const double2 wv = tl_lds2(ring + stage * TL_BRING_ROW_BYTES + 512);
+      stage = (stage + 1 == D) ? 0 : stage + 1;
+      fill = (fill + 1 == D) ? 0 : fill + 1;
+      rv.x = rv.x - alpha * wv.x;
+      rv.y = rv.y - alpha * wv.y;
+      tl_st2_hint(r + (long)j * g.pitch + m.i0, rv, pol_r);
+      acc0 += rv.x * rv.x;
+      acc0 += rv.y * rv.y;
+      if (tiled) tl_push_edges(P.push_r, g, m, j, rv);
     }
     tl_cp_wait<0>();
+  } else if (m.acta) {   // the single last cell of an odd-width tile
+    for (int j = m.j0; j < m.j1; j++) {
+      const long o = (long)j * g.pitch + m.i0;
+      const double v = tl_ld1<COH>(r + o) - alpha * tl_ld1<COH>(w + o);
+      r[o] = v;
+      acc0 += v * v;
+      if (tiled) tl_push_edges(P.push_r, g, m, j, make_double2(v, 0.0));
+    }
   }
+}
+
+template <int D, int MINB>
+__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_r_ring(const CgBParams P) {
+  tl_pdl_entry();
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  __shared__ double sm[32];
+  SolveState *st = P.st;
+  const int it = st->iter;
+  const double rr_cur = st->red_rr;
+  if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
+  const double pw = st->red_pw;
+  const double alpha = rr_cur / pw;
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_pw[it + 1] = pw;
+  double acc[1] = {0.0};
+  tl_cg_b_item_ring<D, false>(P, alpha, blockIdx.x, ring_raw, acc[0]);
   if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
-    st->red_pw_local = acc[0];
-    if (P.single || tiled) st->red_pw = acc[0];
+    st->red_rr_local = acc[0];
+    if (P.single || P.cd != nullptr) st->red_rr = acc[0];
+    st->iter = it + 1;
   }
 }
 

@@ -345,6 +345,65 @@ def test_run_to_run_determinism():
     assert outs[0][1:] == outs[1][1:]
 
 
+@pytest.mark.parametrize("nx,ny,solver,over", [
+    (64, 64, "cg", {}), (200, 120, "cg", {}), (257, 19, "cg", {}), (1, 40, "cg", {}), (3, 3, "cg", {}),
+    (700, 523, "cg", {"maxiters": 500}), (2048, 1536, "cg", {"maxiters": 150}),     # more work items than resident CTAs
+    (128, 128, "cheby", {}), (96, 160, "ppcg", {"ppcginnersteps": 6})])              # CG presteps of the other solvers
+def test_persistent_cg_is_bit_identical(nx, ny, solver, over):
+    """Option cg_persist: the CG loop as ONE persistent cooperative kernel (tl_kernels_persist.cuh).
+    Same work items, same per-item block sums, same fixed summation order: iteration counts,
+    alpha/beta histories and every field are bit-identical to the two-kernels-per-iteration path."""
+    outs = []
+    for persist in (0, 1):
+        s = classic_settings(nx, ny=ny, steps=2, solver=solver, **over)
+        chunk, geom = tl.initialiseapp(s, backend=_device())
+        chunk.set_option("cg_persist", persist)
+        recs, final = tl.diffuse(chunk, s, geom)
+        outs.append(([r["iters"] for r in recs], [r["error"] for r in recs], final["temp"],
+                     {f: chunk.get_field(f) for f in ("u", "energy", "p", "r", "w")},
+                     chunk.cgalpha.copy(), chunk.cgbeta.copy(), [r["kernel_launches"] for r in recs]))
+        chunk.close()
+    a, b = outs
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2], (a[:3], b[:3])
+    for f in a[3]:
+        np.testing.assert_array_equal(a[3][f], b[3][f], err_msg=f)
+    np.testing.assert_array_equal(a[4], b[4])
+    np.testing.assert_array_equal(a[5], b[5])
+    if solver == "cg":
+        assert max(b[6]) < min(a[6])          # one launch for the whole loop instead of two per iteration
+
+
+@pytest.mark.parametrize("depth", [6, 8])
+@pytest.mark.parametrize("nx,ny", [(200, 120), (257, 19), (1, 40), (700, 523)])
+def test_kernel_b_ring_is_bit_identical(nx, ny, depth):
+    """Option b_ring: kernel B with the cp.async ring instead of register batches -- same rows, same
+    arithmetic, same summation order."""
+    outs = []
+    for d in (0, depth):
+        s = classic_settings(nx, ny=ny, steps=1, solver="cg", maxiters=400)
+        chunk, geom = tl.initialiseapp(s, backend=_device())
+        chunk.set_option("b_ring", d)
+        recs, final = tl.diffuse(chunk, s, geom)
+        outs.append((recs[0]["iters"], recs[0]["error"], final["temp"], chunk.get_field("u"), chunk.get_field("r"),
+                     chunk.cgalpha.copy()))
+        chunk.close()
+    a, b = outs
+    assert a[:3] == b[:3]
+    for x, y in zip(a[3:], b[3:]):
+        np.testing.assert_array_equal(x, y)
+
+
+def test_persistent_cg_matches_oracle_through_env_default(monkeypatch):
+    monkeypatch.setenv("TEALEAF_B200_OPTS", "cg_persist=1")
+    s = lambda: classic_settings(150, ny=90, steps=2, solver="cg")
+    dev = run(_device(), s())
+    ora = run(_oracle(), s())
+    assert_parity(dev, ora, fields=("u", "energy", "u0", "kx", "ky"), aux=("p", "w"))
+    monkeypatch.setenv("TEALEAF_B200_OPTS", "no_such_option=1")
+    with pytest.raises(Exception):
+        tl.initialiseapp(s(), backend=_device())
+
+
 @pytest.mark.parametrize("idx", range(12))
 def test_golden(idx):
     with open(GOLDEN) as fh:

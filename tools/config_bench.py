@@ -31,8 +31,9 @@ def main():
     ap.add_argument("--tile", type=int, default=0, help="cells per GPU per side (weak scaling)")
     ap.add_argument("--max-iters", type=int, default=1000)
     ap.add_argument("--inner", type=int, default=10)
-    ap.add_argument("--ppcg-halo-depth", type=int, default=0,
-                    help="PPCG: tile exchange every k inner steps (0 = halo_depth; 1 = every step)")
+    ap.add_argument("--ppcg-halo-depth", default="0",
+                    help="PPCG: tile exchange every k inner steps (0 = halo_depth; 1 = every step); a comma list "
+                         "times every depth in one process")
     ap.add_argument("--halo-depth", type=int, default=2)
     ap.add_argument("--comm", default="fused,nccl")
     ap.add_argument("--reps", type=int, default=2)
@@ -61,12 +62,13 @@ def main():
     else:
         nx = ny = args.glob or 4096
     over = {"maxiters": args.max_iters, "halodepth": args.halo_depth}
-    if args.solver == "ppcg":
-        over["ppcginnersteps"] = args.inner
-        over["ppcghalodepth"] = args.ppcg_halo_depth
-    s = classic_settings(nx, ny=ny, steps=1, solver=args.solver, **over)
+    depths = [int(k) for k in str(args.ppcg_halo_depth).split(",")] if args.solver == "ppcg" else [0]
     comms = args.comm.split(",") if world > 1 else ["single"]
-    for comm in comms:
+    for comm, depth in [(cm, k) for cm in comms for k in depths]:
+        if args.solver == "ppcg":
+            over["ppcginnersteps"] = args.inner
+            over["ppcghalodepth"] = depth
+        s = classic_settings(nx, ny=ny, steps=1, solver=args.solver, **over)
         if world > 1:
             chunk, geom, _ = tld.create_tile(s, dist, local_rank, options={"comm_fused": 1 if comm == "fused" else 0})
         else:

@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Target of tools/sanitize.sh: every kernel family of libtealeaf_b200 once, on meshes small enough
+for compute-sanitizer (memcheck / racecheck / synccheck slow kernels down 10-100x).  Odd sizes on
+purpose: partial strips, a single last column, chunks shorter than the ring depth."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+import tealeaf_jl_b200 as tl  # noqa: E402
+from conftest import classic_settings  # noqa: E402
+from tealeaf_jl_b200.device import DeviceChunk  # noqa: E402
+
+CASES = [("cg", 97, 61, {}, {}), ("cg", 130, 40, {}, {"cg_persist": 1}), ("cg", 75, 90, {}, {"b_ring": 6}),
+         ("cg", 64, 33, {}, {"b_ring": 8}), ("cheby", 97, 61, {}, {}), ("ppcg", 97, 61, {"ppcginnersteps": 4}, {}),
+         ("jacobi", 50, 45, {"maxiters": 120}, {}), ("cg", 1, 40, {}, {}), ("cg", 200, 3, {"halodepth": 3}, {})]
+
+
+def main():
+    for solver, nx, ny, over, opts in CASES:
+        s = classic_settings(nx, ny=ny, steps=1, solver=solver, **over)
+        chunk, geom = tl.initialiseapp(s, backend=DeviceChunk)          # device-side state painter
+        for k, v in opts.items():
+            chunk.set_option(k, v)
+        recs, final = tl.diffuse(chunk, s, geom)                        # fused solve + finalise + field summary
+        u = chunk.get_field("u")
+        assert np.isfinite(u).all()
+        print(f"sanitize target: {solver} {nx}x{ny} {opts} iters={recs[0]['iters']} temp={final['temp']:.12g}", flush=True)
+        chunk.close()
+    # the per-function entry points (kernels.jl / CG.jl names) on one more odd mesh
+    s = classic_settings(70, ny=50, steps=1, solver="cg")
+    chunk, geom = tl.initialiseapp(s, backend=DeviceChunk)
+    recs, final = tl.diffuse(chunk, s, geom, stepwise=True)
+    print(f"sanitize target: stepwise cg 70x50 iters={recs[0]['iters']}", flush=True)
+    chunk.close()
+    print("sanitize target OK")
+
+
+if __name__ == "__main__":
+    main()
