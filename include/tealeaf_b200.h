@@ -80,7 +80,20 @@ int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_depth, int max
 void tl_destroy(tl_ctx *ctx);
 const char *tl_last_error(const tl_ctx *ctx);
 int tl_abi_version(void);
-/* tuning knob (name = "chunk_rows", "blocks_per_sm", "graph_iters", "l2_pin_mb", ...) */
+/* Tuning / A-B knobs; none of them changes a result bit (tests/test_gpu_parity.py).  Defaults are
+ * the measured best.  The environment variable TEALEAF_B200_OPTS
+ * ("name=value,name=value") applies options to every context the process creates.
+ *   chunk_rows, pw_chunk_rows   rows per warp task of the stencil / pointwise kernels (-1 = auto)
+ *   ring_stages                 cp.async ring depth of the stencil kernels: -1 auto, 3, 4, 6
+ *   graph_iters, use_graph      iterations per CUDA graph launch (8) / plain launches instead
+ *   b_reverse                   kernel B walks the tile top-down (1)
+ *   b_ring                      kernel B flavour: 0 register batches (default), 6 / 8 cp.async ring
+ *   cg_persist                  1: the CG loop of a single tile as ONE persistent cooperative kernel
+ *   hint_keep, hint_stream, l2_persist_mb, l2_hit_scale, l2_persist_field    L2 policy experiments
+ *   use_pdl                     programmatic dependent launch between the loop kernels
+ *   comm_fused                  tiles: 1 halo pushes + mailbox sums inside the kernels (default), 0 NCCL + pull kernels
+ *   ppcg_halo_depth             tiles: exchange every k PPCG inner steps (0 = halo_depth)
+ * Unknown names return TL_ERR_ARG. */
 int tl_set_option(tl_ctx *ctx, const char *name, double value);
 
 /* ---- multi-GPU wiring (no counterpart in the reference: it has a single Chunk) ---- */
