@@ -114,6 +114,7 @@ struct tl_ctx {
   bool comm_ready = false;
   int use_pdl = 0;          // programmatic dependent launch between the kernels of the iteration loops: measured
                             // SLOWER (profiles/r01d_pdl_sweep.log: 1024^2 CG 24.7 -> 27.6 us/iteration), kept as an option
+  int balanced_tiling = 1;  // mid-size tiles: chunk length chosen so that every SM holds exactly two CTAs (compute_tiling)
   int b_ring = 0;           // kernel B flavour: 0 = register batches of 4 rows; 6 / 8 = cp.async ring of that depth (4 / 3 CTAs per SM)
   int cg_persist = 0;       // 1: the CG loop of a single tile runs as ONE persistent cooperative kernel (tl_kernels_persist.cuh)
   PersistSync *psync = nullptr;
@@ -212,6 +213,26 @@ static void compute_tiling(tl_ctx *c) {
   int cr = (int)std::min<long>(8, std::max<long>(1, warp_rows / ((long)c->num_sms * bps * 4)));
   int pcr = (int)std::min<long>(16, std::max<long>(1, warp_rows / ((long)c->num_sms * c->pw_blocks_per_sm * 4)));
   if (pcr >= 4) pcr &= ~3;   // the pointwise kernels are unrolled by 4 rows
+  // Mid-size tiles (what a 4096^2 mesh becomes on 4-8 GPUs: 1024^2 ... 2048 x 1024 cells) are only one
+  // or two waves of CTAs, so the wave quantisation decides: 512 CTAs on 444 slots run as two waves, and
+  // 412 CTAs leave some SMs with 3 and others with 2.  Measured (profiles/r01e_tile_sweep.log): exactly
+  // TWO CTAs on every SM, with chunks as long as that takes (up to 16 rows), is fastest there
+  // (2048 x 1024: kernel A 32.8 -> 28.3 us, PPCG inner 26.6 -> 22.6 us, B 11.3 -> 10.3 us).
+  if (c->balanced_tiling) {
+    const int wpb = TL_FUSED_THREADS / 32, nstrips = (g.nx + TL_STRIP - 1) / TL_STRIP;
+    const long slots = 2L * c->num_sms;
+    auto balanced = [&](int quantum) -> int {
+      long r = std::max<long>(1, (warp_rows + slots * wpb - 1) / (slots * wpb));
+      if (quantum > 1 && r >= quantum - 1) r = (r + quantum - 1) / quantum * quantum;
+      for (; r <= 16; r += (r >= quantum ? quantum : 1)) {
+        const long nchunks = (g.ny + r - 1) / r;
+        if ((nstrips * nchunks + wpb - 1) / wpb <= slots) return (int)r;
+      }
+      return 0;   // the tile is several waves whatever the chunk length: keep the streaming defaults
+    };
+    if (const int r = balanced(1)) cr = r;
+    if (const int r = balanced(4)) pcr = r;
+  }
   if (c->chunk_rows >= 0) cr = c->chunk_rows;
   if (c->pw_chunk_rows >= 0) pcr = c->pw_chunk_rows;
   make_tiling(c, bps, cr, &c->tiling, &c->fused_grid);
@@ -429,6 +450,7 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "comm_fused") c->comm_fused = value != 0.0;
   else if (n == "use_pdl") c->use_pdl = value != 0.0;
   else if (n == "cg_persist") c->cg_persist = value != 0.0;
+  else if (n == "balanced_tiling") c->balanced_tiling = value != 0.0;
   else if (n == "b_ring") {
     const int d = (int)value;
     if (d != 0 && d != 6 && d != 8) return tl_fail(c, TL_ERR_ARG, "b_ring must be 0, 6 or 8");
