@@ -114,6 +114,12 @@ struct tl_ctx {
   bool comm_ready = false;
   int use_pdl = 0;          // programmatic dependent launch between the kernels of the iteration loops: measured
                             // SLOWER (profiles/r01d_pdl_sweep.log: 1024^2 CG 24.7 -> 27.6 us/iteration), kept as an option
+  int cheby_pair = 0;       // 1: single tile -- reduction-free Chebyshev iterations run two per pass (k_cheby_pair_ring)
+  int pair_rows = 32;       // rows per warp task of the pair kernel (two redundant rows per task)
+  Tiling pair_tiling{};
+  int pair_grid = 0;
+  cudaGraphExec_t g_cheby2 = nullptr;
+  int g_cheby2_iters = 0;
   int balanced_tiling = 1;  // mid-size tiles: chunk length chosen so that every SM holds exactly two CTAs (compute_tiling)
   int b_ring = 0;           // kernel B flavour: 0 = register batches of 4 rows; 6 / 8 = cp.async ring of that depth (4 / 3 CTAs per SM)
   int cg_persist = 0;       // 1: the CG loop of a single tile runs as ONE persistent cooperative kernel (tl_kernels_persist.cuh)
@@ -240,6 +246,19 @@ static void compute_tiling(tl_ctx *c) {
   const long cells = (long)(g.nx + 2 * g.hd) * (g.ny + 2 * g.hd);
   long nb = (cells + TL_BASIC_THREADS - 1) / TL_BASIC_THREADS;
   c->basic_grid = (int)std::max(1L, std::min<long>(nb, (long)c->num_sms * 8));
+  {  // the two-iteration Chebyshev kernel: 60 owned columns per warp, long chunks (2 redundant rows each)
+    const int wpb = TL_FUSED_THREADS / 32;
+    Tiling t;
+    t.nstrips = (g.nx + TL_PAIR_OWN - 1) / TL_PAIR_OWN;
+    const long wr = (long)t.nstrips * g.ny;
+    long r = std::min<long>(c->pair_rows, std::max<long>(8, wr / (2L * c->num_sms * wpb)));   // small tiles: >= 2 CTAs per SM first
+    r = std::max<long>(r, ((long)t.nstrips * g.ny + (long)TL_MAX_GRID * wpb - 1) / ((long)TL_MAX_GRID * wpb));   // bounded partials array
+    r = std::min<long>(std::max<long>(r, 1), g.ny);
+    t.rows_per_chunk = (int)r;
+    t.nchunks = (g.ny + t.rows_per_chunk - 1) / t.rows_per_chunk;
+    c->pair_tiling = t;
+    c->pair_grid = (t.nstrips * t.nchunks + wpb - 1) / wpb;
+  }
 }
 
 // Decomposition of the tile extended by k-1 cells towards its neighbour tiles (k_ppcg_inner_dk):
@@ -297,6 +316,7 @@ static int apply_l2_policy(tl_ctx *c) {
 static void destroy_graphs(tl_ctx *c) {
   if (c->g_cg) { cudaGraphExecDestroy(c->g_cg); c->g_cg = nullptr; }
   if (c->g_cheby) { cudaGraphExecDestroy(c->g_cheby); c->g_cheby = nullptr; }
+  if (c->g_cheby2) { cudaGraphExecDestroy(c->g_cheby2); c->g_cheby2 = nullptr; }
   if (c->g_ppcg) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
   if (c->g_jacobi) { cudaGraphExecDestroy(c->g_jacobi); c->g_jacobi = nullptr; }
 }
@@ -451,6 +471,8 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "use_pdl") c->use_pdl = value != 0.0;
   else if (n == "cg_persist") c->cg_persist = value != 0.0;
   else if (n == "balanced_tiling") c->balanced_tiling = value != 0.0;
+  else if (n == "cheby_pair") c->cheby_pair = value != 0.0;
+  else if (n == "pair_rows") c->pair_rows = std::max(2, (int)value);
   else if (n == "b_ring") {
     const int d = (int)value;
     if (d != 0 && d != 6 && d != 8) return tl_fail(c, TL_ERR_ARG, "b_ring must be 0, 6 or 8");
@@ -982,13 +1004,14 @@ __global__ void k_state_cheby(SolveState *st, double theta, double eps, int tt0,
   st->theta = theta;
   st->eps_cheby = eps;
   st->cheby_step = 0;
-  st->cheby_done = 0;
+  st->cheby_pairs = 0;
   st->cheby_est = INT_MAX;
   st->cheby_tt0 = tt0;
   st->cheby_max_tt = max_tt;
   st->counter = 0u;
 }
 __global__ void k_state_set_est(SolveState *st, int est) { st->cheby_est = est; }
+__global__ void k_state_set_step(SolveState *st, int step) { st->cheby_step = step; st->cheby_pairs = 0; }
 
 static CgAParams cg_a_params(tl_ctx *c) {
   CgAParams P;
@@ -1305,6 +1328,7 @@ static ChebyParams cheby_params(tl_ctx *c) {
   P.w = c->buf[TL_W]; P.r = c->buf[TL_R]; P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
   P.single = c->nranks == 1;
   P.cd = comm_dev(c); P.push_ua = push_for(c, TL_U); P.push_ub = push_for(c, B_U1);
+  P.p1 = c->buf[B_P1];
   return P;
 }
 
@@ -1321,6 +1345,31 @@ static int enqueue_cheby_iteration(tl_ctx *c) {
   if (legacy) TRY(allreduce2(c, &c->st->red_norm_local, &c->st->red_norm, 1));
   c->launches++;
   return TL_OK;
+}
+
+// Two Chebyshev iterations = one kernel (single tile, option cheby_pair; k_cheby_pair_ring).
+template <int S, int MINB>
+static int launch_cheby_pair_ring(tl_ctx *c, const ChebyParams &P) {
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_cheby_pair_ring<S, MINB>, smem, &prepared));
+  CU(c, tl_launch(c, k_cheby_pair_ring<S, MINB>, c->pair_grid, TL_FUSED_THREADS, smem, P));
+  return TL_OK;
+}
+static int enqueue_cheby_pair(tl_ctx *c) {
+  ChebyParams P = cheby_params(c);
+  P.t = c->pair_tiling;
+  TRY((launch_cheby_pair_ring<4, 2>(c, P)));
+  CHECK_LAUNCH(c);
+  c->launches++;
+  return TL_OK;
+}
+// may the next kernel be a pair?  (the host's copy of the kernel's entry conditions)
+static bool cheby_pair_allowed(const SolveState &s) {
+  if (tl_cheby_should_stop(s)) return false;
+  const int ttA = s.cheby_tt0 + s.cheby_step - 1;
+  if (ttA + 1 > s.cheby_max_tt) return false;
+  return !tl_cheby_is_norm_iter(s.cheby_step, s.cheby_tt0, s.cheby_est);
 }
 
 // common switch bookkeeping of Cheby.solve!/PPCG.solve! (Cheby.jl:25-29, PPCG.jl:25-30)
@@ -1391,8 +1440,21 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
   CHECK_LAUNCH(c);
   auto enq = [&]() { return enqueue_cheby_iteration(c); };
   auto stop = [&](const SolveState &s) { return tl_cheby_should_stop(s); };
-  TRY(run_chunks(c, &c->g_cheby, &c->g_cheby_iters, c->graph_iters, 1, enq, stop, &fin));
-  c->u_cur = fin.cheby_step & 1;
+  bool done = false;
+  if (c->cheby_pair && c->nranks == 1) {
+    // Norm iterations have odd tt (Cheby.jl:40-51: (tt+1) % 10 == 0), so pairs that start on an even tt
+    // never have one as their first half: one single step aligns, then pairs run until the stop rule fires
+    // or only one permitted iteration is left; single steps finish.
+    const int tt_next = (cgit + 1) + 2 - 1;   // tt0 + cheby_step - 1 with cheby_step = 2 after the first main step
+    if (tt_next & 1) TRY(enqueue_cheby_iteration(c));
+    auto enq2 = [&]() { return enqueue_cheby_pair(c); };
+    auto stop2 = [&](const SolveState &s) { return !cheby_pair_allowed(s); };
+    TRY(run_chunks(c, &c->g_cheby2, &c->g_cheby2_iters, std::max(1, c->graph_iters / 2), 1, enq2, stop2, &fin));
+    done = tl_cheby_should_stop(fin);
+  }
+  if (!done) TRY(run_chunks(c, &c->g_cheby, &c->g_cheby_iters, c->graph_iters, 1, enq, stop, &fin));
+  c->u_cur = (fin.cheby_step + fin.cheby_pairs) & 1;
+  c->p_cur = fin.cheby_pairs & 1;
   if (legacy_comm(c)) {   // haloupdate!(.., [:u]) of the last iteration on the tile-internal sides
     TRY(pull_halo(c, c->u_cur ? B_U1 : TL_U, 1));
     TRY(tile_barrier(c));
@@ -1400,6 +1462,10 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
   if (c->u_cur) {
     LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[B_U1], c->buf[TL_U]);
     c->u_cur = 0;
+  }
+  if (c->p_cur) {   // interior only: the Chebyshev iterations never touch p's halo (it stays as CG left it)
+    LAUNCH_BASIC(c, k_copy, c->g, 0, c->buf[B_P1], c->buf[TL_P]);
+    c->p_cur = 0;
   }
   finish_timing(c, info, l0);
   info->cheby_iters = fin.cheby_step - 1;
@@ -1707,7 +1773,7 @@ __global__ void k_state_for_timing(SolveState *st, double *hist_rr, double *hist
   st->iter = 2;
   st->red_rr = 1.0; st->red_pw = 1e300;
   hist_rr[1] = 1.0; hist_rr[2] = 1.0; hist_pw[2] = 1e300; hist_pw[3] = 1e300;
-  st->theta = 1.0; st->eps_cheby = 0.0; st->cheby_step = 1; st->cheby_done = 0; st->cheby_est = INT_MAX;
+  st->theta = 1.0; st->eps_cheby = 0.0; st->cheby_step = 1; st->cheby_pairs = 0; st->cheby_est = INT_MAX;
   st->cheby_tt0 = 1; st->cheby_max_tt = INT_MAX; st->inner_steps = INT_MAX; st->inner_pp = 0; st->counter = 0u;
   for (int i = 0; i < n; i++) { cha[i] = 0.5; chb[i] = 1e-3; }
 }
@@ -1724,13 +1790,16 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
     else if (k == "cg_fused_w_nou") TRY(launch_cg_a<false>(c));
     else if (k == "cg_fused_r") TRY(launch_cg_b(c));
     else if (k == "cheby_fused") TRY(launch_cheby<false>(c));
+    else if (k == "cheby_pair") { TRY(enqueue_cheby_pair(c)); c->launches--; }
     else if (k == "ppcg_inner") TRY(launch_ppcg_inner(c));
     else return tl_fail(c, TL_ERR_ARG, "tl_time_kernel: unknown kernel %s", kernel);
     c->launches++;
     return TL_OK;
   };
+  if (k == "cheby_pair") k_state_set_step<<<1, 1, 0, c->stream>>>(c->st, 2);   // step 1 is a norm iteration: pairs start at 2
   for (int i = 0; i < 3; i++) TRY(launch());
   CHECK_LAUNCH(c);
+  if (k == "cheby_pair") { reps = std::min(reps, (c->max_iters - 16) / 2); k_state_set_step<<<1, 1, 0, c->stream>>>(c->st, 2); }
   if (k == "cg_fused_r") {  // B advances the iteration counter: rewind it
     k_state_for_timing<<<1, 1, 0, c->stream>>>(c->st, c->hist_rr, c->hist_pw, c->ch_alphas, c->ch_betas, c->max_iters);
   }

@@ -50,7 +50,7 @@ struct SolveState {
   StopCfg cfg;
   int iter;             // completed CG-type iterations (CG.jl:18 `tt`, PPCG outer included)
   int cheby_step;       // completed Chebyshev kernels (init counts as step 0 -> 1)
-  int cheby_done;       // (unused: the stop rule is a pure function of the state)
+  int cheby_pairs;      // two-iteration Chebyshev kernels executed in this solve (buffer parity, tl_cheby_u_parity)
   int cheby_est;        // Cheby.calciter estimate (uploaded by the host after the first step)
   int cheby_tt0;        // outer iteration number `tt` of Chebyshev step 1
   int cheby_max_tt;     // maxiters

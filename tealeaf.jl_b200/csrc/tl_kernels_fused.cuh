@@ -275,7 +275,12 @@ struct ChebyParams {
   int single;   // 1: one tile, the kernel publishes its norm itself
   const CommDev *cd;
   Push push_ua, push_ub;
+  double *p1;   // ping-pong partner of p: the two-iteration kernel (k_cheby_pair_ring) writes p out of place
 };
+// Which buffers hold the current u / p: every kernel flips u, the two-iteration kernel also flips p
+// and advances the step counter by two -- hence the parity of (steps + pair kernels) for u and of
+// the pair kernels alone for p (SolveState::cheby_pairs; always 0 without the pair kernel).
+__device__ __forceinline__ int tl_cheby_u_parity(int step, int pairs) { return (step + pairs) & 1; }
 
 // Was Chebyshev step `chebyiters` (1-based) a norm iteration?  Cheby.jl:40-51
 __host__ __device__ inline bool tl_cheby_is_norm_iter(int chebyiters, int tt0, int est) {

@@ -393,6 +393,34 @@ def test_kernel_b_ring_is_bit_identical(nx, ny, depth):
         np.testing.assert_array_equal(x, y)
 
 
+@pytest.mark.parametrize("nx,ny,over", [(128, 128, {}), (96, 160, {}), (65, 70, {}), (257, 19, {}), (61, 300, {}),
+                                        (700, 523, {"maxiters": 900}), (1500, 1100, {"maxiters": 1100}),
+                                        (128, 128, {"maxiters": 77}), (128, 128, {"maxiters": 78})])   # last permitted iteration: first / second half of a pair
+def test_cheby_pair_is_bit_identical(nx, ny, over):
+    """Option cheby_pair: two Chebyshev iterations per pass (k_cheby_pair_ring, temporal blocking).  The
+    intermediate u', p' never reach memory and are recomputed redundantly at warp-task borders with
+    the same expressions on the same inputs: every field is bit-identical to one kernel per iteration."""
+    outs = []
+    for pair in (0, 1):
+        s = classic_settings(nx, ny=ny, steps=2, solver="cheby", **over)
+        chunk, geom = tl.initialiseapp(s, backend=_device())
+        chunk.set_option("cheby_pair", pair)
+        recs, final = tl.diffuse(chunk, s, geom)
+        outs.append(([(r["iters"], r["cg_iters"], r["cheby_iters"], r["est_iters"]) for r in recs], [r["error"] for r in recs],
+                     final["temp"], {f: chunk.get_field(f) for f in ("u", "energy", "p", "w", "r")},
+                     [r["kernel_launches"] for r in recs]))
+        chunk.close()
+    a, b = outs
+    assert a[0] == b[0], (a[0], b[0])
+    for f in a[3]:
+        np.testing.assert_array_equal(a[3][f], b[3][f], err_msg=f)
+    assert a[2] == b[2]
+    for ea, eb in zip(a[1], b[1]):               # the norm is summed over different warp tasks
+        assert abs(ea - eb) <= 1e-10 * abs(ea)
+    if max(r[2] for r in a[0]) > 20:
+        assert sum(b[4]) < sum(a[4])             # fewer launches: two iterations per kernel
+
+
 def test_persistent_cg_matches_oracle_through_env_default(monkeypatch):
     monkeypatch.setenv("TEALEAF_B200_OPTS", "cg_persist=1")
     s = lambda: classic_settings(150, ny=90, steps=2, solver="cg")
