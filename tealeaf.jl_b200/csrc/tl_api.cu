@@ -102,7 +102,7 @@ struct tl_ctx {
   int dk_grid = 0, dk_k = 1, dk_rows_per_chunk = 0;
   int ppcg_depth_k = 0;           // option "ppcg_halo_depth": 0 = auto (halo_depth)
   cudaGraphExec_t g_cg = nullptr, g_cheby = nullptr, g_ppcg = nullptr, g_jacobi = nullptr;
-  int g_cg_iters = 0, g_cheby_iters = 0, g_ppcg_iters = 0, g_ppcg_inner = 0, g_ppcg_k = 0, g_jacobi_iters = 0;
+  int g_cg_iters = 0, g_cheby_iters = 0, g_ppcg_iters = 0, g_ppcg_inner = 0, g_ppcg_k = 0, g_ppcg_pairs = 0, g_jacobi_iters = 0;
   long long launches = 0;
   // peers (tile-internal sides): 0 left, 1 right, 2 bottom, 3 top
   int nbr_rank[4] = {-1, -1, -1, -1};
@@ -114,7 +114,8 @@ struct tl_ctx {
   bool comm_ready = false;
   int use_pdl = 0;          // programmatic dependent launch between the kernels of the iteration loops: measured
                             // SLOWER (profiles/r01d_pdl_sweep.log: 1024^2 CG 24.7 -> 27.6 us/iteration), kept as an option
-  int cheby_pair = 0;       // 1: single tile -- reduction-free Chebyshev iterations run two per pass (k_cheby_pair_ring)
+  int ppcg_pair = 1;        // 1: single tile, even inner_steps -- PPCG inner steps run two per pass (k_ppcg_pair_ring)
+  int cheby_pair = 1;       // 1: single tile -- reduction-free Chebyshev iterations run two per pass (k_cheby_pair_ring)
   int pair_rows = 32;       // rows per warp task of the pair kernel (two redundant rows per task)
   Tiling pair_tiling{};
   int pair_grid = 0;
@@ -472,6 +473,7 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "cg_persist") c->cg_persist = value != 0.0;
   else if (n == "balanced_tiling") c->balanced_tiling = value != 0.0;
   else if (n == "cheby_pair") c->cheby_pair = value != 0.0;
+  else if (n == "ppcg_pair") c->ppcg_pair = value != 0.0;
   else if (n == "pair_rows") c->pair_rows = std::max(2, (int)value);
   else if (n == "b_ring") {
     const int d = (int)value;
@@ -1540,8 +1542,44 @@ static PpcgInnerParams ppcg_inner_params(tl_ctx *c) {
 // reads through the stencil (p'; sd0; sd'; r after the last inner step) and ends with the tile
 // exchange.  Legacy mode: depth-1 halo pulls -- r, p before the matvec (ordered by the preceding rr
 // allreduce) and sd before every inner step (ordered by a 1-double NCCL rendezvous).
+// does this context run the inner steps two per pass?
+static bool ppcg_pairs_enabled(const tl_ctx *c, int inner_steps) {
+  return c->ppcg_pair && c->nranks == 1 && inner_steps >= 2 && (inner_steps % 2) == 0;
+}
+template <int S, int MINB>
+static int launch_ppcg_pair_ring(tl_ctx *c, const PpcgPairParams &P) {
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_ppcg_pair_ring<S, MINB>, smem, &prepared));
+  CU(c, tl_launch(c, k_ppcg_pair_ring<S, MINB>, c->pair_grid, TL_FUSED_THREADS, smem, P));
+  return TL_OK;
+}
+// pair k of the npairs pairs of an outer iteration: sd alternates TL_SD / B_SD1 from TL_SD (where
+// k_ppcg_ur_sd writes it); r alternates TL_R / B_R1 phased so that the LAST pair writes TL_R
+static PpcgPairParams ppcg_pair_params(tl_ctx *c, int k, int npairs) {
+  PpcgPairParams P;
+  P.g = c->g; P.t = c->pair_tiling; P.st = c->st; P.alphas = c->ch_alphas; P.betas = c->ch_betas;
+  P.sin = c->buf[(k & 1) ? B_SD1 : TL_SD];
+  P.sout = c->buf[(k & 1) ? TL_SD : B_SD1];
+  P.rin = c->buf[((npairs - k) & 1) ? B_R1 : TL_R];
+  P.rout = c->buf[((npairs - 1 - k) & 1) ? B_R1 : TL_R];
+  P.u = c->buf[TL_U]; P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
+  return P;
+}
+
 static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k) {
   const bool legacy = legacy_comm(c);
+  if (ppcg_pairs_enabled(c, inner_steps)) {
+    const int npairs = inner_steps / 2;
+    TRY(launch_cg_a<false>(c));
+    PpcgUrParams U = ppcg_ur_params(c);
+    if (npairs & 1) { U.deep = 1; U.r_out = c->buf[B_R1]; U.d_sd = 1; U.d_r = 0; }   // r goes where the first pair reads it
+    CU(c, tl_launch(c, k_ppcg_ur_sd, c->pw_grid, TL_FUSED_THREADS, 0, U));
+    for (int k = 0; k < npairs; k++) TRY((launch_ppcg_pair_ring<4, 2>(c, ppcg_pair_params(c, k, npairs))));
+    CHECK_LAUNCH(c);
+    c->launches += 2 + npairs;
+    return TL_OK;
+  }
   if (depth_k > 1) {
     // matrix-powers groups: one tile exchange per depth_k inner steps (PpcgDkParams)
     TRY(launch_cg_a<false>(c));
@@ -1643,9 +1681,12 @@ extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double e
   if (c->g_ppcg && (c->g_ppcg_inner != inner_steps || c->g_ppcg_k != depth_k)) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
   c->g_ppcg_inner = inner_steps;
   c->g_ppcg_k = depth_k;
-  TRY(run_chunks(c, &c->g_ppcg, &c->g_ppcg_iters, chunk, 2 + inner_steps, enq, stop, &fin));
+  const bool pairs = ppcg_pairs_enabled(c, inner_steps);
+  if (c->g_ppcg && c->g_ppcg_pairs != (int)pairs) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
+  c->g_ppcg_pairs = pairs;
+  TRY(run_chunks(c, &c->g_ppcg, &c->g_ppcg_iters, chunk, pairs ? 2 + inner_steps / 2 : 2 + inner_steps, enq, stop, &fin));
   TRY(cg_flush(c, fin.iter, false));
-  c->sd_cur = (depth_k > 1 ? (inner_steps + depth_k - 1) / depth_k : inner_steps) & 1;
+  c->sd_cur = (pairs ? inner_steps / 2 : depth_k > 1 ? (inner_steps + depth_k - 1) / depth_k : inner_steps) & 1;
   if (c->sd_cur) {
     LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[B_SD1], c->buf[TL_SD]);
     c->sd_cur = 0;
@@ -1791,6 +1832,7 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
     else if (k == "cg_fused_r") TRY(launch_cg_b(c));
     else if (k == "cheby_fused") TRY(launch_cheby<false>(c));
     else if (k == "cheby_pair") { TRY(enqueue_cheby_pair(c)); c->launches--; }
+    else if (k == "ppcg_pair") TRY((launch_ppcg_pair_ring<4, 2>(c, ppcg_pair_params(c, 0, 2))));
     else if (k == "ppcg_inner") TRY(launch_ppcg_inner(c));
     else return tl_fail(c, TL_ERR_ARG, "tl_time_kernel: unknown kernel %s", kernel);
     c->launches++;
@@ -1799,6 +1841,7 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
   if (k == "cheby_pair") k_state_set_step<<<1, 1, 0, c->stream>>>(c->st, 2);   // step 1 is a norm iteration: pairs start at 2
   for (int i = 0; i < 3; i++) TRY(launch());
   CHECK_LAUNCH(c);
+  if (k == "ppcg_pair") reps = std::min(reps, (c->max_iters - 16) / 2);
   if (k == "cheby_pair") { reps = std::min(reps, (c->max_iters - 16) / 2); k_state_set_step<<<1, 1, 0, c->stream>>>(c->st, 2); }
   if (k == "cg_fused_r") {  // B advances the iteration counter: rewind it
     k_state_for_timing<<<1, 1, 0, c->stream>>>(c->st, c->hist_rr, c->hist_pw, c->ch_alphas, c->ch_betas, c->max_iters);

@@ -375,6 +375,21 @@ struct PpcgInnerParams {
   Push push_sda, push_sdb, push_r;
 };
 
+// TWO inner steps in one pass (k_ppcg_pair_ring, tl_kernels_ring.cuh; single tile, even inner_steps):
+//   step A (pp):    rA = r - A sd ;   uA = u + sd ;   sA = alpha_pp sd + beta_pp rA
+//   step B (pp+1):  rB = rA - A sA ;  uB = uA + sA ;  sB = alpha_pp+1 sA + beta_pp+1 rB
+// ~32 B per cell-step instead of 64.  sA is recomputed redundantly at warp-task borders (needs the
+// OLD r there, so r is ping-ponged like sd); the host gives every pair of an outer iteration its
+// own in/out buffers, phased so that the last pair leaves r in the Chunk's own buffer.
+struct PpcgPairParams {
+  Geo g; Tiling t;
+  SolveState *st;
+  const double *alphas; const double *betas;
+  const double *sin; double *sout; const double *rin; double *rout;
+  double *u; const double *kx; const double *ky;
+  double *partials;
+};
+
 // Matrix-powers variant of the inner steps for tiles (k_ppcg_inner_dk): the steps are grouped by
 // k = the halo depth of the exchange.  A group starts with sd valid k cells deep in the
 // tile-internal halos (r: k-1 cells; kx, ky pulled once per solve), step q of the group computes

@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
 #define TL_PAIR_OWN 60   // owned columns per warp (window: 64)
 template <int S, int MINB>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_ring(const ChebyParams P) {
+  tl_pdl_entry();
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
@@ -592,6 +593,118 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_ring(cons
     }
     st->cheby_step = step + 2;
     st->cheby_pairs = pairs + 1;
+  }
+}
+
+// Two PPCG inner steps in one pass (algorithm: PpcgPairParams in tl_kernels_fused.cuh; window,
+// carry and clamp scheme: k_cheby_pair_ring above).
+template <int S, int MINB>
+__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_pair_ring(const PpcgPairParams P) {
+  tl_pdl_entry();
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  __shared__ double sm[32];
+  SolveState *st = P.st;
+  const int it = st->iter;
+  if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
+  const int pp = st->inner_pp;
+  const bool last = (pp + 2 == st->inner_steps);
+  const double alphaA = P.alphas[pp], betaA = P.betas[pp];
+  const double alphaB = P.alphas[pp + 1], betaB = P.betas[pp + 1];
+  const double *__restrict__ sin = P.sin;
+  double *__restrict__ sout = P.sout;
+  const double *__restrict__ rin = P.rin;
+  double *__restrict__ rout = P.rout;
+  const double *__restrict__ kx = P.kx;
+  const double *__restrict__ ky = P.ky;
+  double *u = P.u;
+  const Geo g = P.g;
+  const int pitch = g.pitch;
+  const bool physL = g.phys & TL_PHYS_LEFT, physR = g.phys & TL_PHYS_RIGHT;
+  const bool physB = g.phys & TL_PHYS_BOTTOM, physT = g.phys & TL_PHYS_TOP;
+
+  double acc[1] = {0.0};
+  const int lane = threadIdx.x & 31;
+  const int wt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wt < P.t.nstrips * P.t.nchunks) {
+    const int s = wt % P.t.nstrips, q = wt / P.t.nstrips;
+    const int j0 = q * P.t.rows_per_chunk, j1 = min(g.ny, j0 + P.t.rows_per_chunk);
+    const int own_lo = s * TL_PAIR_OWN, own_hi = min(g.nx, own_lo + TL_PAIR_OWN);
+    MarchCtx m;                            // the WINDOW
+    m.lane = lane;
+    m.i0 = own_lo - 2 + 2 * lane;
+    m.j0 = j0; m.j1 = j1;
+    m.ld_ok = m.i0 <= g.nx;
+    m.acta = m.ld_ok;
+    m.actb = m.ld_ok;
+    m.ecol = 0; m.has_edge = false;
+    MarchCtx mo = m;                       // the OWNED cells
+    mo.acta = m.i0 >= own_lo && m.i0 < own_hi;
+    mo.actb = m.i0 + 1 >= own_lo && m.i0 + 1 < own_hi && mo.acta;
+    if (j0 < j1) {
+      const double2 z2 = make_double2(0.0, 0.0);
+      const int ja_lo = (j0 == 0 && physB) ? 0 : j0 - 1;
+      const int ja_hi = (j1 == g.ny && physT) ? g.ny - 1 : j1;
+      RingMarch<S> rg;
+      rg.init(ring_raw, m);
+      double2 Sm, Sc, kyc;
+      {
+        const int jm = (ja_lo == 0 && physB) ? 0 : ja_lo - 1;
+        const long om = (long)jm * pitch + m.i0, oc = (long)ja_lo * pitch + m.i0;
+        Sm = m.ld_ok ? tl_ld2(sin + om) : z2;
+        Sc = m.ld_ok ? tl_ld2(sin + oc) : z2;
+        kyc = m.ld_ok ? tl_ld2(ky + oc) : z2;
+      }
+#pragma unroll
+      for (int d = 0; d < S - 1; d++) {
+        if (ja_lo + d <= ja_hi) rg.issue(g, m, physT, ja_lo + d, d, sin, ky, kx, rin, u);
+        tl_cp_commit();
+      }
+      // carried for step B on row j = jj - 1: sA(j-1), sA(j), rA(j), uA(j), kx(j), ky(j)
+      double2 Am = z2, Ac = z2, rAc = z2, uAc = z2, kxc = z2, kyB = z2;
+      auto step_b = [&](int j, double2 An, double2 kyn) {
+        const double2 Bm = (j == 0 && physB) ? Ac : Am;
+        double wa, wb;
+        tl_stencil2(g, m, physL, physR, Bm, Ac, An, 0.0, kxc, 0.0, kyB, kyn, wa, wb);
+        const double2 rn = make_double2(rAc.x - wa, rAc.y - wb);
+        const double2 un = make_double2(uAc.x + Ac.x, uAc.y + Ac.y);
+        const double2 sn = make_double2(alphaB * Ac.x + betaB * rn.x, alphaB * Ac.y + betaB * rn.y);
+        const long oc = (long)j * pitch + m.i0;
+        if (mo.actb) {
+          tl_st2(rout + oc, rn); tl_st2(u + oc, un); tl_st2(sout + oc, sn);
+          acc[0] += rn.x * rn.x;
+          acc[0] += rn.y * rn.y;
+        } else if (mo.acta) {
+          rout[oc] = rn.x; u[oc] = un.x; sout[oc] = sn.x;
+          acc[0] += rn.x * rn.x;
+        }
+        // halo(sd) of PPCG.jl:76 happens BEFORE each inner step (see k_ppcg_inner_ring)
+        tl_reflect_edges(sout, g, mo, j, oc, last ? Ac : sn);
+      };
+      for (int jj = ja_lo; jj <= ja_hi; jj++) {
+        if (jj + S - 1 <= ja_hi) rg.issue(g, m, physT, jj + S - 1, rg.fill, sin, ky, kx, rin, u);
+        tl_cp_commit();
+        tl_cp_wait<S - 1>();
+        const RingRow cur = rg.take(m, true, true);      // x = sd(jj+1), ky(jj+1), kx(jj), a = r(jj), b = u(jj)
+        double wa, wb;
+        tl_stencil2(g, m, physL, physR, Sm, Sc, cur.x, 0.0, cur.kx, 0.0, kyc, cur.ky, wa, wb);
+        const double2 rA = make_double2(cur.a.x - wa, cur.a.y - wb);
+        const double2 uA = make_double2(cur.b.x + Sc.x, cur.b.y + Sc.y);
+        const double2 sA = make_double2(alphaA * Sc.x + betaA * rA.x, alphaA * Sc.y + betaA * rA.y);
+        if (jj - 1 >= j0) step_b(jj - 1, sA, kyc);
+        Am = Ac; Ac = sA; rAc = rA; uAc = uA; kxc = cur.kx; kyB = kyc;
+        Sm = Sc; Sc = cur.x; kyc = cur.ky;
+      }
+      if (ja_hi == j1 - 1) step_b(j1 - 1, Ac, kyc);
+      tl_cp_wait<0>();
+    }
+  }
+  if (tl_kernel_tail(acc, last, st, P.partials, nullptr, sm)) {
+    if (last) {
+      st->red_rr_local = acc[0];      // PPCG.jl:88
+      st->red_rr = acc[0];
+      st->iter = it + 1;
+    }
+    st->inner_pp = pp + 2;
   }
 }
 

@@ -421,6 +421,34 @@ def test_cheby_pair_is_bit_identical(nx, ny, over):
         assert sum(b[4]) < sum(a[4])             # fewer launches: two iterations per kernel
 
 
+@pytest.mark.parametrize("nx,ny,inner,over", [(128, 128, 10, {}), (96, 160, 4, {}), (65, 70, 6, {}), (257, 19, 2, {}), (61, 300, 10, {}),
+                                              (700, 523, 10, {"maxiters": 700}), (1500, 1100, 8, {"maxiters": 900})])
+def test_ppcg_pair_is_bit_identical(nx, ny, inner, over):
+    """Option ppcg_pair: two PPCG inner steps per pass (k_ppcg_pair_ring).  Per-cell arithmetic is identical
+    to one kernel per inner step; the outer iteration's sum(r.r) is added up over different warp tasks and
+    feeds beta, so whole solves agree to the rounding of that sum (iteration counts identical, fields
+    1e-11 of max|u|), not bit for bit."""
+    outs = []
+    for pair in (0, 1):
+        s = classic_settings(nx, ny=ny, steps=2, solver="ppcg", ppcginnersteps=inner, **over)
+        chunk, geom = tl.initialiseapp(s, backend=_device())
+        chunk.set_option("ppcg_pair", pair)
+        recs, final = tl.diffuse(chunk, s, geom)
+        outs.append(([(r["iters"], r["cg_iters"], r["cheby_iters"], r["inner_total"]) for r in recs], [r["error"] for r in recs],
+                     final["temp"], {f: chunk.get_field(f) for f in ("u", "energy", "p", "sd", "w")},
+                     [r["kernel_launches"] for r in recs]))
+        chunk.close()
+    a, b = outs
+    assert a[0] == b[0], (a[0], b[0])
+    for ea, eb in zip(a[1], b[1]):               # a converged residual norm is rounding noise of the sums: observed 2e-8
+        assert abs(ea - eb) <= 1e-5 * abs(ea)
+    # the outer recurrence consumes the (differently summed) norm, so fields agree to rounding of the sums, not bitwise
+    scale = np.abs(a[3]["u"]).max()
+    for f in a[3]:
+        assert np.abs(a[3][f] - b[3][f]).max() <= 1e-11 * scale, f
+    assert abs(a[2] - b[2]) <= 1e-12 * abs(a[2])
+
+
 def test_persistent_cg_matches_oracle_through_env_default(monkeypatch):
     monkeypatch.setenv("TEALEAF_B200_OPTS", "cg_persist=1")
     s = lambda: classic_settings(150, ny=90, steps=2, solver="cg")
