@@ -80,7 +80,9 @@ int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_depth, int max
 void tl_destroy(tl_ctx *ctx);
 const char *tl_last_error(const tl_ctx *ctx);
 int tl_abi_version(void);
-/* Tuning / A-B knobs; none of them changes a result bit (tests/test_gpu_parity.py).  Defaults are
+/* Tuning / A-B knobs.  None of them changes per-cell arithmetic; those that change how the tile is cut into
+ * warp tasks (chunk_rows, balanced_tiling, *_pair) change the order dot products are added up in
+ * (tests/test_gpu_parity.py states what stays bit-identical).  Defaults are
  * the measured best.  The environment variable TEALEAF_B200_OPTS
  * ("name=value,name=value") applies options to every context the process creates.
  *   chunk_rows, pw_chunk_rows   rows per warp task of the stencil / pointwise kernels (-1 = auto)
@@ -89,6 +91,9 @@ int tl_abi_version(void);
  *   b_reverse                   kernel B walks the tile top-down (1)
  *   b_ring                      kernel B flavour: 0 register batches (default), 6 / 8 cp.async ring
  *   cg_persist                  1: the CG loop of a single tile as ONE persistent cooperative kernel
+ *   cheby_pair, ppcg_pair       single tile: two Chebyshev iterations / PPCG inner steps per pass (default 1)
+ *   pair_rows                   rows per warp task of the pair kernels (32)
+ *   balanced_tiling             mid-size tiles: chunk length that puts exactly two CTAs on every SM (default 1)
  *   hint_keep, hint_stream, l2_persist_mb, l2_hit_scale, l2_persist_field    L2 policy experiments
  *   use_pdl                     programmatic dependent launch between the loop kernels
  *   comm_fused                  tiles: 1 halo pushes + mailbox sums inside the kernels (default), 0 NCCL + pull kernels
