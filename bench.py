@@ -14,7 +14,9 @@ Prints ONE JSON line (rank 0).  `value` = cells x iterations / device time with 
 resident in HBM; `e2e` = the same through the C-ABI with HOST buffers, uploads of that step's
 inputs and the download of its result inside the timed region.  `--impl reference` times the
 CPU oracle (the reference is Julia and cannot run here) with all host threads
-on a bounded sample of the same workload.
+on a bounded sample of the same workload.  At N = 1 the line also carries `other_configs`: the
+Chebyshev iteration and the PPCG inner step (configs[2], configs[3]) timed alone on the same tile,
+one and two iterations per pass.
 """
 from __future__ import annotations
 
@@ -333,6 +335,28 @@ def run_b200(args):
                       "frac_of_nominal_8TBs": CG_ALG_BYTES * tile_cells / (it_ms * 1e-3) / 1e9 / 8000.0},
     }
 
+    # ---- the reduction-free iterations of configs[2] / configs[3] on the same tile (kernels timed alone) ----
+    other = None
+    if world == 1:
+        try:
+            def per_it(name, its_per_launch):
+                ms = min(chunk.time_kernel(name, 30) for _ in range(2))
+                return 1e3 * ms / its_per_launch
+            c1, c2 = per_it("cheby_fused", 1), per_it("cheby_pair", 2)
+            p1, p2 = per_it("ppcg_inner", 1), per_it("ppcg_pair", 2)
+            other = {
+                "note": "kernels of BASELINE.json configs[2]/[3] timed alone on this 4096x4096 tile (CUDA events, 30 launches); "
+                        "two_per_pass = temporal blocking (k_cheby_pair_ring / k_ppcg_pair_ring), the default on a single tile",
+                "chebyshev_iteration": {"one_per_pass_us": c1, "two_per_pass_us": c2, "algorithmic_bytes_per_cell": 88,
+                                        "cell_iterations_per_s": tile_cells / (c2 * 1e-6),
+                                        "algorithmic_gbs": 88 * tile_cells / (c2 * 1e-6) / 1e9},
+                "ppcg_inner_step": {"one_per_pass_us": p1, "two_per_pass_us": p2, "algorithmic_bytes_per_cell": 80,
+                                    "cell_steps_per_s": tile_cells / (p2 * 1e-6),
+                                    "algorithmic_gbs": 80 * tile_cells / (p2 * 1e-6) / 1e9},
+            }
+        except Exception as e:      # never let the side measurement break the headline line
+            other = {"error": repr(e)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle.oracle import load
@@ -363,6 +387,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": field_bytes + 32, "ms_per_step": 1e3 * e2e_wall / args.steps,
                     "host_numa_binding": numa},
             "gpu_launches": int(launches), "clocks": clocks,
+            **({"other_configs": other} if other else {}),
             **({"same_tile_single_gpu": {"value": solo, "unit": UNIT, "note":
                 "this rank's tile solved alone (1x1, 60 CG iterations incl. init) in the same job; "
                 "weak-scaling efficiency of the N-GPU workload = value / (N x this)"}} if solo else {}),
