@@ -67,6 +67,17 @@ end
 
 Base.size(c::B200Chunk) = (c.x, c.y)
 
+"""
+    set_option!(chunk, name, value)
+
+Tuning / A-B knob of the library (`tl_set_option`, the list is in include/tealeaf_b200.h): e.g.
+`set_option!(chunk, "cheby_pair", 0)` runs one Chebyshev iteration per kernel instead of two.
+The environment variable `TEALEAF_B200_OPTS="name=value,..."` does the same for every context.
+"""
+function set_option!(chunk::B200Chunk, name::AbstractString, value::Real)
+    check(chunk, ccall((:tl_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Cdouble), chunk.ctx, name, Float64(value)))
+end
+
 # ---- field transfer: getfield/setfield of Chunk matrices -------------------------------------
 function upload!(chunk::B200Chunk, field::Symbol, a::Matrix{Float64})
     size(a) == size(chunk) || throw(DimensionMismatch("field $(field)"))

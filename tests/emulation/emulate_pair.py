@@ -108,6 +108,9 @@ def run(nx, ny, rpc, hd=2):
     print(f"{nx}x{ny} rows/chunk {rpc}: bit-identical = {ok}", flush=True)
     assert ok
 
-for nx, ny, rpc in [(7, 5, 2), (60, 9, 4), (61, 6, 3), (64, 8, 8), (121, 7, 2), (1, 6, 3), (130, 1, 4), (59, 10, 32), (3, 3, 1), (120, 4, 1)]:
-    run(nx, ny, rpc)
-print("emulation OK")
+CASES = [(7, 5, 2), (60, 9, 4), (61, 6, 3), (64, 8, 8), (121, 7, 2), (1, 6, 3), (130, 1, 4), (59, 10, 32), (3, 3, 1), (120, 4, 1)]
+
+if __name__ == "__main__":
+    for nx, ny, rpc in CASES:
+        run(nx, ny, rpc)
+    print("emulation OK")

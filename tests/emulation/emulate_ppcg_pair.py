@@ -1,12 +1,9 @@
 """NumPy emulation of k_ppcg_pair_ring's carry logic vs two single inner steps (bit for bit)."""
 import numpy as np
-import importlib.util, sys, os
-spec = importlib.util.spec_from_file_location("ep", os.path.join(os.path.dirname(__file__), "emulate_pair.py"))
-# reuse helpers without running its main: exec only the function definitions
-src = open(os.path.join(os.path.dirname(__file__), "emulate_pair.py")).read().split("def run(")[0]
-ns = {}
-exec(src, ns)
-stencil_full, stencil2 = ns["stencil_full"], ns["stencil2"]
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emulate_pair import stencil_full, stencil2  # noqa: E402
 rng = np.random.default_rng(7)
 
 def single_inner(sd, r, u, kx, ky, nx, ny, hd, al, be):
@@ -62,7 +59,10 @@ def pair_kernel(sd, r, u, kx, ky, nx, ny, hd, aA, bA, aB, bB, rpc, OWN=60):
                 step_b(j1 - 1, Ac, kyc)
     return sout, rout, uo
 
-for nx, ny, rpc in [(7, 5, 2), (61, 6, 3), (121, 7, 2), (1, 6, 3), (130, 1, 4), (59, 10, 32), (120, 4, 1)]:
+CASES = [(7, 5, 2), (61, 6, 3), (121, 7, 2), (1, 6, 3), (130, 1, 4), (59, 10, 32), (120, 4, 1)]
+
+
+def run(nx, ny, rpc):
     hd = 2
     shape = (ny + 2 * hd, nx + 2 * hd + 70)
     f = lambda: rng.standard_normal(shape)
@@ -75,4 +75,9 @@ for nx, ny, rpc in [(7, 5, 2), (61, 6, 3), (121, 7, 2), (1, 6, 3), (130, 1, 4), 
     ok = np.array_equal(so[I], s2[I]) and np.array_equal(ro[I], r2[I]) and np.array_equal(uo[I], u2[I])
     print(f"{nx}x{ny} rows/chunk {rpc}: bit-identical = {ok}")
     assert ok
-print("ppcg pair emulation OK")
+
+
+if __name__ == "__main__":
+    for nx, ny, rpc in CASES:
+        run(nx, ny, rpc)
+    print("ppcg pair emulation OK")
