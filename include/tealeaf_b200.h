@@ -93,6 +93,7 @@ int tl_abi_version(void);
  *   cg_persist                  1: the CG loop of a single tile as ONE persistent cooperative kernel
  *   cheby_pair, ppcg_pair       single tile: two Chebyshev iterations / PPCG inner steps per pass (default 1)
  *   pair_rows                   rows per warp task of the pair kernels (32)
+ *   pair_tiled                  EXPERIMENTAL, default 0, not yet run on a GPU: Chebyshev pairs on tiles (one exchange per two iterations)
  *   balanced_tiling             mid-size tiles: chunk length that puts exactly two CTAs on every SM (default 1)
  *   hint_keep, hint_stream, l2_persist_mb, l2_hit_scale, l2_persist_field    L2 policy experiments
  *   use_pdl                     programmatic dependent launch between the loop kernels

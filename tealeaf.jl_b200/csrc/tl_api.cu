@@ -114,6 +114,7 @@ struct tl_ctx {
   bool comm_ready = false;
   int use_pdl = 0;          // programmatic dependent launch between the kernels of the iteration loops: measured
                             // SLOWER (profiles/r01d_pdl_sweep.log: 1024^2 CG 24.7 -> 27.6 us/iteration), kept as an option
+  int pair_tiled = 0;       // EXPERIMENTAL (not yet run on a GPU): Chebyshev pairs on tiles, one rendezvous per two iterations
   int ppcg_pair = 1;        // 1: single tile, even inner_steps -- PPCG inner steps run two per pass (k_ppcg_pair_ring)
   int cheby_pair = 1;       // 1: single tile -- reduction-free Chebyshev iterations run two per pass (k_cheby_pair_ring)
   int pair_rows = 32;       // rows per warp task of the pair kernel (two redundant rows per task)
@@ -474,6 +475,7 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "balanced_tiling") c->balanced_tiling = value != 0.0;
   else if (n == "cheby_pair") c->cheby_pair = value != 0.0;
   else if (n == "ppcg_pair") c->ppcg_pair = value != 0.0;
+  else if (n == "pair_tiled") c->pair_tiled = value != 0.0;
   else if (n == "pair_rows") c->pair_rows = std::max(2, (int)value);
   else if (n == "b_ring") {
     const int d = (int)value;
@@ -1366,6 +1368,47 @@ static int enqueue_cheby_pair(tl_ctx *c) {
   c->launches++;
   return TL_OK;
 }
+// EXPERIMENTAL: the pair kernel on tiles (option pair_tiled; k_cheby_pair_tiled_ring)
+static bool cheby_pairs_tiled(const tl_ctx *c) {
+  if (!(c->cheby_pair && c->pair_tiled && c->nranks > 1 && c->comm_fused && c->g.hd >= 2)) return false;
+  for (int r = 0; r < c->nranks; r++)
+    if (c->rank_blob[r].nx < 2 || c->rank_blob[r].ny < 2) return false;
+  return true;
+}
+template <int S, int MINB>
+static int launch_cheby_pair_tiled_ring(tl_ctx *c, const ChebyPairTiledParams &P) {
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_cheby_pair_tiled_ring<S, MINB>, smem, &prepared));
+  CU(c, tl_launch(c, k_cheby_pair_tiled_ring<S, MINB>, c->pair_grid, TL_FUSED_THREADS, smem, P));
+  return TL_OK;
+}
+static int enqueue_cheby_pair_tiled(tl_ctx *c) {
+  ChebyPairTiledParams P;
+  P.c = cheby_params(c);
+  P.c.t = c->pair_tiling;
+  P.push_ua = push8_for(c, TL_U); P.push_ub = push8_for(c, B_U1);
+  P.push_p0 = push8_for(c, TL_P); P.push_p1 = push8_for(c, B_P1);
+  TRY((launch_cheby_pair_tiled_ring<4, 2>(c, P)));
+  CHECK_LAUNCH(c);
+  c->launches++;
+  return TL_OK;
+}
+// halos the first pair reads: kx, ky, u0, p and the current u two cells deep, corner blocks included, plus
+// the neighbours' physical-top halo row in the tile-internal halo columns (ky(.., ny))
+static int cheby_pair_tiled_fill_halos(tl_ctx *c, int u_buf) {
+  const int bufs[5] = {TL_KX, TL_KY, TL_U0, TL_P, u_buf};
+  TRY(tile_barrier(c));
+  TRY(pull_halo_wide(c, bufs, 5, 2));
+  for (int q = 0; q < 5; q++) {
+    k_pull_halo_cols_top<<<1, 32, 0, c->stream>>>(c->g, 2, c->buf[bufs[q]], peer_face(c, 0, bufs[q]), peer_face(c, 1, bufs[q]));
+    c->launches++;
+    CHECK_LAUNCH(c);
+  }
+  TRY(tile_barrier(c));
+  return TL_OK;
+}
+
 // may the next kernel be a pair?  (the host's copy of the kernel's entry conditions)
 static bool cheby_pair_allowed(const SolveState &s) {
   if (tl_cheby_should_stop(s)) return false;
@@ -1443,13 +1486,18 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
   auto enq = [&]() { return enqueue_cheby_iteration(c); };
   auto stop = [&](const SolveState &s) { return tl_cheby_should_stop(s); };
   bool done = false;
-  if (c->cheby_pair && c->nranks == 1) {
+  const bool tiled_pairs = cheby_pairs_tiled(c);
+  if ((c->cheby_pair && c->nranks == 1) || tiled_pairs) {
     // Norm iterations have odd tt (Cheby.jl:40-51: (tt+1) % 10 == 0), so pairs that start on an even tt
     // never have one as their first half: one single step aligns, then pairs run until the stop rule fires
     // or only one permitted iteration is left; single steps finish.
     const int tt_next = (cgit + 1) + 2 - 1;   // tt0 + cheby_step - 1 with cheby_step = 2 after the first main step
     if (tt_next & 1) TRY(enqueue_cheby_iteration(c));
-    auto enq2 = [&]() { return enqueue_cheby_pair(c); };
+    if (tiled_pairs) {
+      const int step_now = 2 + (tt_next & 1);                       // cheby_step after the alignment step
+      TRY(cheby_pair_tiled_fill_halos(c, (step_now & 1) ? B_U1 : TL_U));   // the buffer the first pair reads (no pair ran yet)
+    }
+    auto enq2 = [&]() { return tiled_pairs ? enqueue_cheby_pair_tiled(c) : enqueue_cheby_pair(c); };
     auto stop2 = [&](const SolveState &s) { return !cheby_pair_allowed(s); };
     TRY(run_chunks(c, &c->g_cheby2, &c->g_cheby2_iters, std::max(1, c->graph_iters / 2), 1, enq2, stop2, &fin));
     done = tl_cheby_should_stop(fin);

@@ -329,6 +329,20 @@ __global__ void k_pull_halo_wide(Geo g, int depth, int phase, double *f, PeerFac
   }
 }
 
+// Phase 0 of k_pull_halo_wide extended upwards by one row on a PHYSICAL top: the neighbour's own halo row ny
+// (ky there is what the stencil of row ny-1 reads) -- needed by kernels that recompute cells in the
+// tile-internal halo columns next to a physical top (k_cheby_pair_tiled_ring; found by
+// tests/emulation/emulate_pair_tiled.py).  EXPERIMENTAL, with that kernel.
+__global__ void k_pull_halo_cols_top(Geo g, int depth, double *f, PeerFace left, PeerFace right) {
+  if (!(g.phys & TL_PHYS_TOP)) return;
+  const int total = 2 * depth;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int side = t / depth, d = t % depth + 1, j = g.ny;
+    if (side == 0) { if (left.f0)  f[(long)j * g.pitch - d] = __ldcv(&left.f0[(long)j * left.pitch + left.nx - d]); }
+    else           { if (right.f0) f[(long)j * g.pitch + g.nx + d - 1] = __ldcv(&right.f0[(long)j * right.pitch + d - 1]); }
+  }
+}
+
 // kernels.jl:119-133 (+ upstream vol/mass/ie): cell_mass = volume*density;
 // vol += volume; mass += cell_mass; ie += cell_mass*energy0; temp += cell_mass*u.
 __global__ void k_field_summary(Geo g, double cell_volume, const double *__restrict__ density,
