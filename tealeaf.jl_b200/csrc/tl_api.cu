@@ -256,10 +256,13 @@ static void compute_tiling(tl_ctx *c) {
     long r = std::min<long>(c->pair_rows, std::max<long>(8, wr / (2L * c->num_sms * wpb)));   // small tiles: >= 2 CTAs per SM first
     r = std::max<long>(r, ((long)t.nstrips * g.ny + (long)TL_MAX_GRID * wpb - 1) / ((long)TL_MAX_GRID * wpb));   // bounded partials array
     r = std::min<long>(std::max<long>(r, 1), g.ny);
-    t.rows_per_chunk = (int)r;
-    t.nchunks = (g.ny + t.rows_per_chunk - 1) / t.rows_per_chunk;
+    for (;; r++) {   // the rounding of the bound above can leave a few CTAs too many
+      t.rows_per_chunk = (int)r;
+      t.nchunks = (g.ny + t.rows_per_chunk - 1) / t.rows_per_chunk;
+      c->pair_grid = (t.nstrips * t.nchunks + wpb - 1) / wpb;
+      if (c->pair_grid <= TL_MAX_GRID || r >= g.ny) break;
+    }
     c->pair_tiling = t;
-    c->pair_grid = (t.nstrips * t.nchunks + wpb - 1) / wpb;
   }
 }
 
