@@ -14,9 +14,11 @@ Prints ONE JSON line (rank 0).  `value` = cells x iterations / device time with 
 resident in HBM; `e2e` = the same through the C-ABI with HOST buffers, uploads of that step's
 inputs and the download of its result inside the timed region.  `--impl reference` times the
 CPU oracle (the reference is Julia and cannot run here) with all host threads
-on a bounded sample of the same workload.  At N = 1 the line also carries `other_configs`: the
-Chebyshev iteration and the PPCG inner step (configs[2], configs[3]) timed alone on the same tile,
-one and two iterations per pass.
+on a bounded sample of the same workload (and never loads the CUDA library).  Every line also carries
+`other_configs`: BASELINE.json configs[2] (Chebyshev, 4096 x 4096 global) and configs[3] (PPCG, 8192 x 8192
+global, tile exchange every step vs every `halo_depth` steps) solved once on the N GPUs (strong scaling), and at
+N = 1 `weak_tile_16384`: the 16384 x 16384 tile of the N > 1 workload solved alone, the like-for-like base of
+the weak-scaling efficiency.
 """
 from __future__ import annotations
 
@@ -30,7 +32,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
@@ -98,7 +99,7 @@ class ClockSampler:
 
 
 def classic(nx, ny, steps, maxiters=10000, solver="cg"):
-    from conftest import classic_settings
+    from tealeaf_jl_b200.decks import classic_settings
     return classic_settings(nx, ny=ny, steps=steps, solver=solver, maxiters=maxiters)
 
 
@@ -129,7 +130,10 @@ def cpu_cg_sample(n, iters, threads, reps=1):
 
 def run_reference(args):
     """--impl reference: the CPU implementation of the path (oracle port; the Julia reference
-    cannot execute in this environment) on all host threads, bounded sample per step."""
+    cannot execute in this environment) on all host threads, bounded sample per step.  Never touches
+    the CUDA library.  The metric is per cell-iteration, so the sample is the same at every N: CG
+    iterations on the 4096 x 4096 classic deck (named in config.sample -- at N > 1 the B200 arm's
+    workload is 16384^2 cells per GPU, which the CPU would need 24 GB and minutes per step for)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -139,30 +143,46 @@ def run_reference(args):
     import tealeaf_jl_b200 as tl
     from oracle.oracle import OracleChunk
     s = classic(n, n, 1)
-    chunk, geom = tl.initialiseapp(s, backend=lambda *a, **k: OracleChunk(*a, threads=threads, **k))
-    tl.haloupdate(chunk, s, 1, ["energy", "density"])
     rx, ry = s.dtinit / s.dx ** 2, s.dtinit / s.dy ** 2
 
-    def step():
-        rro = chunk.cg_init(s.coefficient, rx, ry)
-        chunk.haloupdate(["u", "p"], 1)
-        chunk.copyu()
-        t0 = time.perf_counter()
-        chunk.cg_fixed_iters(rro, iters)
-        return time.perf_counter() - t0
+    def make(nthreads):
+        chunk, geom = tl.initialiseapp(s, backend=lambda *a, **k: OracleChunk(*a, threads=nthreads, **k))
+        tl.haloupdate(chunk, s, 1, ["energy", "density"])
 
+        def step(niters):
+            rro = chunk.cg_init(s.coefficient, rx, ry)
+            chunk.haloupdate(["u", "p"], 1)
+            chunk.copyu()
+            t0 = time.perf_counter()
+            chunk.cg_fixed_iters(rro, niters)
+            return time.perf_counter() - t0
+        return chunk, step
+
+    chunk, step = make(threads)
     for _ in range(args.warmup):
-        step()
-    total = sum(step() for _ in range(args.steps))
+        step(iters)
+    total = sum(step(iters) for _ in range(args.steps))
+    chunk.close()
     value = n * n * iters * args.steps / total
-    sample = f"{iters} CG iterations per step of the {n}x{n} classic deck (w!, ur!, p!, halo), OpenMP"
+    # the reference itself is serial (no threading anywhere, CG.jl:82-90): one thread, a shorter sample
+    chunk1, step1 = make(1)
+    step1(2)
+    serial_iters = 6
+    t1 = step1(serial_iters)
+    chunk1.close()
+    serial = n * n * serial_iters / t1
+    sample = f"{iters} CG iterations per step of the {n}x{n} classic deck (w!, ur!, p!, halo), OpenMP oracle, {threads} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus), "solver": "cg", "note":
-                   "CPU oracle port of the reference algorithm (Julia reference not runnable here)"},
+        "config": {"workload": workload_name(args.gpus), "solver": "cg", "sample": sample,
+                   "note": "CPU oracle port of the reference algorithm (the Julia reference is not runnable here); the metric is "
+                           "per cell-iteration, so the bounded CPU sample is the 4096x4096 deck at every N"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline_serial": {"value": serial, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{serial_iters} CG iterations of the same deck on one thread ({t1:.1f} s): what the "
+                                          "reference is (no threading anywhere)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))

@@ -101,6 +101,10 @@ int tl_abi_version(void);
  *   ppcg_halo_depth             tiles: exchange every k PPCG inner steps (0 = halo_depth)
  * Unknown names return TL_ERR_ARG. */
 int tl_set_option(tl_ctx *ctx, const char *name, double value);
+/* Read-back of any option above, and of derived quantities: ring_stages_effective (the ring depth in use),
+ * rows_per_chunk / pw_rows_per_chunk / pair_rows_per_chunk and fused_grid / pw_grid / pair_grid (how the tile
+ * is cut into warp tasks and CTAs), max_grid (the bound on a grid: the partials array), num_sms. */
+int tl_get_option(tl_ctx *ctx, const char *name, double *value);
 
 /* ---- multi-GPU wiring (no counterpart in the reference: it has a single Chunk) ---- */
 int tl_comm_blob_size(void);                       /* bytes of one exported blob */

@@ -78,6 +78,13 @@ function set_option!(chunk::B200Chunk, name::AbstractString, value::Real)
     check(chunk, ccall((:tl_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Cdouble), chunk.ctx, name, Float64(value)))
 end
 
+"`tl_get_option`: read-back of an option or a derived quantity (e.g. \"ring_stages_effective\", \"rows_per_chunk\")"
+function get_option(chunk::B200Chunk, name::AbstractString)::Float64
+    v = Ref(0.0)
+    check(chunk, ccall((:tl_get_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Ref{Cdouble}), chunk.ctx, name, v))
+    return v[]
+end
+
 # ---- field transfer: getfield/setfield of Chunk matrices -------------------------------------
 function upload!(chunk::B200Chunk, field::Symbol, a::Matrix{Float64})
     size(a) == size(chunk) || throw(DimensionMismatch("field $(field)"))
@@ -256,7 +263,7 @@ prefers the reference's own painter calls `upload!` with `host.density`, `host.e
 """
 function initialiseapp!(settings::Settings; device::Int = 0)::B200Chunk
     chunk = B200Chunk(settings; device = device)
-    setchunkstate!(chunk, settings)
+    TeaLeaf.setchunkstate!(chunk, settings)   # not exported by the reference (src/chunk.jl:4-7): qualified
     TeaLeaf.Kernels.haloupdate!(chunk, settings, 1, [:density, :energy0, :energy])
     check(chunk, ccall((:tl_copy_field, LIB), Cint, (Ptr{Cvoid}, Cint, Cint), chunk.ctx, FIELD_ID[:energy], FIELD_ID[:energy0]))
     # route `set.solver.solve!` to the device modules

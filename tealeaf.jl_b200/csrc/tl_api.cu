@@ -77,7 +77,7 @@ struct tl_ctx {
   Geo g{};
   int max_iters = 0, device = 0;
   int rank = 0, px = 1, py = 1, cx = 0, cy = 0, nranks = 1;
-  size_t rows = 0, buf_doubles = 0;
+  size_t rows = 0, buf_doubles = 0, hist_len = 0;   // hist_len: doubles in each of hist_rr / hist_pw / ch_alphas / ch_betas
   char *slab = nullptr;
   size_t slab_bytes = 0;
   double *buf[B_COUNT]{};   // interior-origin pointers
@@ -87,7 +87,9 @@ struct tl_ctx {
   SolveState *h_st = nullptr;   // pinned, 2 polling slots
   double *h_scal = nullptr;     // pinned scratch
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[2]{}, ev_start = nullptr, ev_stop = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev[2]{}, ev_start = nullptr, ev_stop = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_phase = nullptr;
+  bool phase_marked = false;
+  double last_cg_ms = 0.0;      // device time of the CG phase (preamble + CG presteps + flush) of the last solve: tl_get_option("last_cg_phase_ms")
   int num_sms = 148;
   // tuning
   int blocks_per_sm = 2, pw_blocks_per_sm = 4, chunk_rows = -1, pw_chunk_rows = -1, graph_iters = 8, use_graph = 1;
@@ -369,6 +371,7 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
   c->buf_doubles = ((c->rows * g.pitch + 31) / 32) * 32;
 
   const size_t hist = ((size_t)max_iters + 8 + 31) / 32 * 32;
+  c->hist_len = hist;
   size_t bytes = (size_t)B_COUNT * c->buf_doubles * sizeof(double);
   const size_t off_state = bytes; bytes += 4096;
   const size_t off_hist = bytes; bytes += 4 * hist * sizeof(double);
@@ -401,7 +404,8 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
       cudaEventCreateWithFlags(&c->ev[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||
-      cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess) {
+      cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess ||
+      cudaEventCreate(&c->ev_phase) != cudaSuccess) {
     g_create_error = cudaGetErrorString(cudaGetLastError());
     tl_destroy(c);
     return TL_ERR_CUDA;
@@ -452,6 +456,7 @@ extern "C" void tl_destroy(tl_ctx *c) {
   if (c->ev_stop) cudaEventDestroy(c->ev_stop);
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->ev_phase) cudaEventDestroy(c->ev_phase);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -502,7 +507,54 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   destroy_graphs(c);
   compute_tiling(c);
   c->dk_grid = 0;   // recomputed by the next depth-k PPCG solve
-  return apply_l2_policy(c);
+  // The L2 carve-out calls synchronise the whole DEVICE: only when an L2 option changed (tiles that share a GPU
+  // must never device-synchronise while another tile's kernel waits for them in a rendezvous).
+  if (n.rfind("l2_", 0) == 0) return apply_l2_policy(c);
+  return TL_OK;
+}
+
+// Read-back of an option or of a derived quantity (what the tests assert the measured code paths on).
+extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
+  if (!c || !name || !value) return TL_ERR_ARG;
+  const std::string n(name);
+  double v;
+  if (n == "blocks_per_sm") v = c->blocks_per_sm;
+  else if (n == "pw_blocks_per_sm") v = c->pw_blocks_per_sm;
+  else if (n == "ring_stages") v = c->ring_stages;
+  else if (n == "ring_stages_effective") v = c->ring_eff;
+  else if (n == "hint_keep") v = c->hint_keep;
+  else if (n == "hint_stream") v = c->hint_stream;
+  else if (n == "b_reverse") v = c->b_reverse;
+  else if (n == "comm_fused") v = c->comm_fused;
+  else if (n == "use_pdl") v = c->use_pdl;
+  else if (n == "cg_persist") v = c->cg_persist;
+  else if (n == "balanced_tiling") v = c->balanced_tiling;
+  else if (n == "cheby_pair") v = c->cheby_pair;
+  else if (n == "ppcg_pair") v = c->ppcg_pair;
+  else if (n == "pair_tiled") v = c->pair_tiled;
+  else if (n == "pair_rows") v = c->pair_rows;
+  else if (n == "b_ring") v = c->b_ring;
+  else if (n == "ppcg_halo_depth") v = c->ppcg_depth_k;
+  else if (n == "l2_persist_mb") v = c->l2_persist_mb;
+  else if (n == "l2_hit_scale") v = c->l2_hit_scale;
+  else if (n == "l2_persist_field") v = c->l2_persist_field;
+  else if (n == "chunk_rows") v = c->chunk_rows;
+  else if (n == "pw_chunk_rows") v = c->pw_chunk_rows;
+  else if (n == "graph_iters") v = c->graph_iters;
+  else if (n == "use_graph") v = c->use_graph;
+  // derived (read-only): how the tile is cut
+  else if (n == "rows_per_chunk") v = c->tiling.rows_per_chunk;
+  else if (n == "pw_rows_per_chunk") v = c->pw_tiling.rows_per_chunk;
+  else if (n == "pair_rows_per_chunk") v = c->pair_tiling.rows_per_chunk;
+  else if (n == "fused_grid") v = c->fused_grid;
+  else if (n == "pw_grid") v = c->pw_grid;
+  else if (n == "pair_grid") v = c->pair_grid;
+  else if (n == "max_grid") v = TL_MAX_GRID;
+  else if (n == "num_sms") v = c->num_sms;
+  else if (n == "last_cg_phase_ms") v = c->last_cg_ms;   // device time of the CG phase of the last solve
+  else return tl_fail(c, TL_ERR_ARG, "unknown option %s", name);
+  *value = v;
+  return TL_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -722,7 +774,7 @@ static int pull_halo_wide(tl_ctx *c, const int *bufs, int nbufs, int depth) {
 // already ordered by a dot-product allreduce.
 static int tile_barrier(tl_ctx *c) {
   if (c->nranks == 1) return TL_OK;
-  return allreduce(c, &c->st->red_aux[3], 1);
+  return allreduce2(c, &c->st->barrier_zero, &c->st->barrier_out, 1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1189,7 +1241,10 @@ static int run_chunks(tl_ctx *c, cudaGraphExec_t *exec, int *exec_iters, int chu
   CU(c, cudaStreamSynchronize(c->stream));
   *final_state = c->h_st[k & 1];
   if (final_state->comm_error)
-    return tl_fail(c, TL_ERR_COMM, "tile exchange timed out: a neighbour tile did not reach the same kernel");
+    return tl_fail(c, TL_ERR_COMM, "tile exchange timed out: tile %d did not hear from tile %d in exchange %llu (a neighbour tile did not "
+                   "reach the same kernel); state: iter %d, cheby_step %d, cheby_pairs %d, inner_pp %d", c->rank,
+                   final_state->comm_error - 1, final_state->xseq, final_state->iter, final_state->cheby_step,
+                   final_state->cheby_pairs, final_state->inner_pp);
   if (!stopped(*final_state)) return tl_fail(c, TL_ERR_STATE, "internal: chunk loop ended before the stop rule fired");
   return TL_OK;
 }
@@ -1301,6 +1356,12 @@ static void finish_timing(tl_ctx *c, tl_solve_info *info, long long launches0) {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop);
   info->solve_ms = ms;
+  c->last_cg_ms = ms;
+  if (c->phase_marked) {
+    float pms = 0.f;
+    if (cudaEventElapsedTime(&pms, c->ev_start, c->ev_phase) == cudaSuccess) c->last_cg_ms = pms;
+    c->phase_marked = false;
+  }
   info->kernel_launches = c->launches - launches0;
 }
 
@@ -1446,6 +1507,8 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
   SolveState fin;
   TRY(cg_phase(c, &fin));
   TRY(cg_flush(c, fin.iter, true));
+  CU(c, cudaEventRecord(c->ev_phase, c->stream));   // end of the CG phase (tl_get_option "last_cg_phase_ms")
+  c->phase_marked = true;
   const int cgit = fin.iter;
   info->cg_iters = cgit;
   info->iters = cgit;
@@ -1676,6 +1739,9 @@ extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double e
                              double epslim, int errorswitch, int inner_steps, int halo_depth_k, tl_solve_info *info) {
   if (!c || !info || inner_steps < 1 || halo_depth_k < 0) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_solve: bad argument");
   if (halo_depth_k > c->g.hd) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_solve: halo_depth_k %d exceeds halo_depth %d", halo_depth_k, c->g.hd);
+  if ((size_t)inner_steps + 2 > c->hist_len)   // the coefficient arrays were sized from max_iters at tl_create
+    return tl_fail(c, TL_ERR_ARG, "tl_ppcg_solve: inner_steps %d does not fit the coefficient arrays (%zu entries, sized from max_iters)",
+                   inner_steps, c->hist_len - 2);
   memset(info, 0, sizeof *info);
   CU(c, cudaSetDevice(c->device));
   if (c->nranks > 1 && !c->comm_ready) return tl_fail(c, TL_ERR_STATE, "tile context used before tl_comm_connect");
@@ -1689,6 +1755,8 @@ extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double e
   SolveState fin;
   TRY(cg_phase(c, &fin));
   TRY(cg_flush(c, fin.iter, true));
+  CU(c, cudaEventRecord(c->ev_phase, c->stream));   // end of the CG phase (tl_get_option "last_cg_phase_ms")
+  c->phase_marked = true;
   const int cgit = fin.iter;
   info->cg_iters = cgit;
   info->iters = cgit;
@@ -1885,6 +1953,7 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
     else if (k == "cheby_pair") { TRY(enqueue_cheby_pair(c)); c->launches--; }
     else if (k == "ppcg_pair") TRY((launch_ppcg_pair_ring<4, 2>(c, ppcg_pair_params(c, 0, 2))));
     else if (k == "ppcg_inner") TRY(launch_ppcg_inner(c));
+    else if (k == "jacobi_fused") { TRY(launch_jacobi(c)); c->launches--; }
     else return tl_fail(c, TL_ERR_ARG, "tl_time_kernel: unknown kernel %s", kernel);
     c->launches++;
     return TL_OK;

@@ -73,6 +73,9 @@ struct SolveState {
   unsigned long long xseq;
   int comm_error;
   int pad1;
+  // tile_barrier(): an out-of-place all-tiles sum of `barrier_zero` (never written: stays 0.0) into
+  // `barrier_out`, so that a rendezvous never accumulates into a slot somebody else uses
+  double barrier_zero, barrier_out;
 };
 
 // ---- multi-GPU: peer-mapped mailboxes and halo push targets --------------------------------
@@ -228,7 +231,7 @@ __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState
       if ((++spins & 1023u) == 0u) {   // a neighbour that never arrives must not hang the GPU
         const unsigned long long t = tl_globaltimer();
         if (t0 == 0) t0 = t;
-        else if (t - t0 > TL_XCHG_TIMEOUT_NS) { st->comm_error = 1; break; }
+        else if (t - t0 > TL_XCHG_TIMEOUT_NS) { st->comm_error = 1 + (int)threadIdx.x; break; }   // 1 + the rank not heard from
       }
     }
     sm[1 + threadIdx.x] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));

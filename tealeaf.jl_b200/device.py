@@ -56,6 +56,11 @@ class DeviceChunk:
     def set_option(self, name: str, value: float):
         self._ck(self._l.tl_set_option(self.ctx, name.encode(), float(value)))
 
+    def get_option(self, name: str) -> float:
+        out = C.c_double()
+        self._ck(self._l.tl_get_option(self.ctx, name.encode(), C.byref(out)))
+        return out.value
+
     # ---- multi-GPU wiring ----
     def comm_export(self) -> bytes:
         buf = C.create_string_buffer(self._l.tl_comm_blob_size())

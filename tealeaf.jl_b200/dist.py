@@ -86,9 +86,11 @@ class ThreadGroup:
             t.start()
         for t in threads:
             t.join()
-        real = [e for e in errors if e is not None and e.__class__.__name__ != "BrokenBarrierError"]
+        real = [(r, e) for r, e in enumerate(errors) if e is not None and e.__class__.__name__ != "BrokenBarrierError"]
+        if len(real) > 1:      # every tile's own story, not just the first one's
+            raise RuntimeError("; ".join(f"[tile {r}] {e}" for r, e in real)) from real[0][1]
         if real or any(errors):
-            raise (real or [e for e in errors if e is not None])[0]
+            raise (real[0][1] if real else [e for e in errors if e is not None][0])
         return results
 
 
@@ -193,6 +195,7 @@ def create_tile(settings: Settings, dist, device: int, backend=None, options=Non
     connect(chunk, dist)
     for k, v in (options or {}).items():
         chunk.set_option(k, v)
+    dist.barrier()       # every tile is wired and configured before the first rendezvous kernel is launched
     geom = HostGeometry(settings, tile=(x0, y0, tnx, tny))
     upload_initial_state(chunk, settings, geom)
     return chunk, geom, (px, py)

@@ -54,6 +54,7 @@ SIGNATURES = {
     "tl_last_error": (C.c_char_p, [_P]),
     "tl_abi_version": (_I, []),
     "tl_set_option": (_I, [_P, C.c_char_p, _D]),
+    "tl_get_option": (_I, [_P, C.c_char_p, _DP]),
     "tl_comm_blob_size": (_I, []),
     "tl_comm_export": (_I, [_P, _P]),
     "tl_comm_unique_id": (_I, [_P]),

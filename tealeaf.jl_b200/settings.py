@@ -82,6 +82,10 @@ class Settings:
     # extension (north_star "depth-k halos"): exchange depth of the PPCG inner steps between tiles,
     # 0 = halo_depth.  Deck key `ppcg_halo_depth` / `tl_ppcg_halo_depth`; no effect on the result.
     ppcghalodepth: int = 0
+    # compatibility switch (Appendix A #6): True reproduces the reference's literal state-geometry nudge,
+    # which always uses the DEFAULT dx = dy = (100 - 0)/10 = 10 because `readstate` runs inside the line
+    # loop and dx, dy are only recomputed after it (src/settings.jl:98-100 vs :132-133)
+    literalnudge: bool = False
 
     def recompute_spacing(self) -> None:
         """src/settings.jl:132-133 (and Appendix A #23 for the -x/-y overrides)."""
@@ -128,14 +132,15 @@ def _apply_nudge(state: State, settings: Settings) -> None:
     raw = state._raw
     if state._num == 1:
         return
+    dx, dy = (10.0, 10.0) if settings.literalnudge else (settings.dx, settings.dy)
     if "xmin" in raw:
-        state.xmin = raw["xmin"] + settings.dx / 100
+        state.xmin = raw["xmin"] + dx / 100
     if "ymin" in raw:
-        state.ymin = raw["ymin"] + settings.dy / 100
+        state.ymin = raw["ymin"] + dy / 100
     if "xmax" in raw:
-        state.xmax = raw["xmax"] - settings.dx / 100
+        state.xmax = raw["xmax"] - dx / 100
     if "ymax" in raw:
-        state.ymax = raw["ymax"] - settings.dy / 100
+        state.ymax = raw["ymax"] - dy / 100
 
 
 def readstate(line: str, settings: Settings) -> State:
@@ -167,9 +172,11 @@ def readstate(line: str, settings: Settings) -> State:
     return state
 
 
-def parse_settings_text(text: str) -> Settings:
-    """`Settings(infile)`, src/settings.jl:90-135, on the text of a deck."""
+def parse_settings_text(text: str, literal_nudge: bool = False) -> Settings:
+    """`Settings(infile)`, src/settings.jl:90-135, on the text of a deck.  `literal_nudge=True` paints
+    the states exactly as the unpatched reference would (see Settings.literalnudge)."""
     settings = Settings()
+    settings.literalnudge = literal_nudge
     state_lines = []
     for rawline in text.splitlines():
         line = rawline.strip()
@@ -209,10 +216,10 @@ def parse_settings_text(text: str) -> Settings:
     return settings
 
 
-def parse_settings(infile: str) -> Settings:
+def parse_settings(infile: str, literal_nudge: bool = False) -> Settings:
     log.info("Reading configuration from %s", infile)
     with open(infile, "r") as fh:
-        return parse_settings_text(fh.read())
+        return parse_settings_text(fh.read(), literal_nudge=literal_nudge)
 
 
 def checkingvalue(settings: Settings, problemfile: str | None = None) -> float:

@@ -161,6 +161,9 @@ class Cheby:
                 if chebyiters == 1:
                     eigmin, eigmax = eigenvalues(chunk.cgalpha, chunk.cgbeta, tt - 1)  # A#14
                     theta, al, be = cheby_coef(eigmin, eigmax, max(settings.maxiters - (tt - 1), 2))
+                    # the reference indexes chebyα[chebyiters+1] in a maxiters-long, zero-initialised vector
+                    # (chunk.jl:86-87): entries past the filled ones read 0.0, as tl_cheby_solve's padding does
+                    al, be = np.concatenate([al, np.zeros(2)]), np.concatenate([be, np.zeros(2)])
                     bb = chunk.cheby_init(theta)
                     resettoexchange(settings)
                     settings.toexchange["u"] = True

@@ -1,0 +1,211 @@
+"""Parity of the kernel instantiations and code paths behind the MEASURED numbers (bench.py, SCALE):
+ring depth 4 / 6, the TL_MAX_GRID clamp of the tiling, plain launches instead of graphs, other graph
+lengths, other chunk lengths, balanced tiling off -- single tile and tiled -- and the pair kernels at
+benchmark-like sizes against the (OpenMP) oracle.  Same bars as tests/test_gpu_parity.py
+(CG.jl:7-29, Cheby.jl:10-61, PPCG.jl:9-55): iteration counts exact (CG: +-1), per-step summaries
+1e-10, u / energy 1e-9.  Needs a B200: -m gpu."""
+import numpy as np
+import pytest
+
+import tealeaf_jl_b200 as tl
+from conftest import classic_settings
+from test_gpu_parity import _device, _oracle, assert_parity, rel, run
+
+pytestmark = pytest.mark.gpu
+
+OPTION_SETS = [
+    {"ring_stages": 4}, {"ring_stages": 6}, {"use_graph": 0}, {"graph_iters": 1}, {"graph_iters": 3},
+    {"chunk_rows": 1}, {"chunk_rows": 5}, {"balanced_tiling": 0}, {"pw_chunk_rows": 3, "b_reverse": 0},
+]
+SOLVER_OVER = {"cg": {}, "cheby": {}, "ppcg": {"ppcginnersteps": 6}, "jacobi": {"maxiters": 150}}
+
+
+def omp_oracle():
+    """The oracle on every host thread: element-wise arithmetic is the serial oracle's, only the dot
+    products are summed per thread (within the 1e-11 the GPU's tree sums are allowed anyway)."""
+    from oracle.oracle import OracleChunk, load
+    threads = load().tlo_max_threads()
+    return lambda *a, **k: OracleChunk(*a, threads=threads, **k)
+
+
+def run_opts(s, opts):
+    chunk, geom = tl.initialiseapp(s, backend=_device())
+    for k, v in opts.items():
+        chunk.set_option(k, v)
+    for k, v in opts.items():
+        assert chunk.get_option(k) == v
+    summaries = []
+    recs, final = tl.diffuse(chunk, s, geom, on_step=lambda rec: summaries.append(chunk.fieldsummary(geom.cell_volume)))
+    return chunk, recs, final, summaries
+
+
+_ORACLE_CACHE = {}
+
+
+def oracle_run(solver, nx, ny, steps):
+    key = (solver, nx, ny, steps)
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE[key] = run(_oracle(), classic_settings(nx, ny=ny, steps=steps, solver=solver, **SOLVER_OVER[solver]))
+    return _ORACLE_CACHE[key]
+
+
+@pytest.mark.parametrize("opts", OPTION_SETS, ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()))
+@pytest.mark.parametrize("solver", ["cg", "cheby", "ppcg", "jacobi"])
+def test_option_variants_match_oracle(solver, opts):
+    """Every tuning option the measured configurations use (or could be switched to) against the oracle."""
+    nx, ny = 131, 150
+    s = classic_settings(nx, ny=ny, steps=2, solver=solver, **SOLVER_OVER[solver])
+    dev = run_opts(s, opts)
+    if "ring_stages" in opts:
+        assert dev[0].get_option("ring_stages_effective") == opts["ring_stages"]
+    if "chunk_rows" in opts:
+        assert dev[0].get_option("rows_per_chunk") == opts["chunk_rows"]
+    assert_parity(dev, oracle_run(solver, nx, ny, 2), iter_slack=1 if solver == "cg" else 0)
+
+
+TILED_OPTION_SETS = [{"ring_stages": 4}, {"ring_stages": 6}, {"use_graph": 0}, {"graph_iters": 3}, {"chunk_rows": 5}, {"balanced_tiling": 0}]
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("opts", TILED_OPTION_SETS, ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()))
+@pytest.mark.parametrize("solver", ["cg", "cheby", "ppcg"])
+def test_option_variants_tiled_match_oracle(solver, opts):
+    from test_tiled_one_gpu import check_against_oracle, run_oracle, run_tiled
+    nx, ny = 150, 131
+    over = SOLVER_OVER[solver]
+    got = run_tiled((2, 2), solver, nx, ny, steps=1, over=over, options=opts)
+    key = ("tiled", solver)
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE[key] = run_oracle(solver, nx, ny, steps=1, over=over)
+    check_against_oracle(got, _ORACLE_CACHE[key], solver)
+
+
+# ---- the pair kernels (temporal blocking) at benchmark-like sizes vs the oracle ---------------------
+@pytest.mark.timeout(1200)
+@pytest.mark.parametrize("n", [1024, 2048])
+@pytest.mark.parametrize("solver", ["cheby", "ppcg"])
+def test_pair_kernels_match_oracle_at_size(solver, n):
+    """Chebyshev / PPCG with two iterations per pass (the default on a single tile) against the OpenMP
+    oracle for one timestep: exact iteration counts, summaries 1e-10, u 1e-9."""
+    s = lambda: classic_settings(n, steps=1, solver=solver)
+    dev = run(_device(), s())
+    assert dev[0].get_option("cheby_pair" if solver == "cheby" else "ppcg_pair") == 1
+    ora = run(omp_oracle(), s())
+    for dr, orr in zip(dev[1], ora[1]):
+        assert dr["cg_iters"] == orr["cg_iters"], (dr, orr)
+        assert dr["cheby_iters"] == orr["cheby_iters"], (dr, orr)
+        assert dr["inner_total"] == orr["inner_total"], (dr, orr)
+        if solver == "cheby":
+            assert dr["est_iters"] == orr["est_iters"]
+    assert_parity(dev, ora, iter_slack=0)
+    # fewer launches than iterations: the pairs really ran
+    r = dev[1][0]
+    sweeps = r["cheby_iters"] if solver == "cheby" else r["inner_total"]
+    assert sweeps > 100 and r["kernel_launches"] < 2 * r["cg_iters"] + 0.75 * sweeps + 400, r
+
+
+# ---- ring depth 4 + the TL_MAX_GRID clamp: what every 16384^2-per-GPU SCALE run executes -----------
+@pytest.mark.timeout(1200)
+def test_ring4_and_grid_clamp_match_oracle_8192():
+    """8192^2 selects ring depth 4 at 2 CTAs/SM automatically and the grid bound clamps the number of row
+    chunks (rows_per_chunk > 8): the same code path as the 16384^2 tiles of the weak-scaling runs.  CG capped at
+    30 iterations against the OpenMP oracle, element-wise."""
+    n, cap = 8192, 30
+    s = lambda: classic_settings(n, steps=1, solver="cg", maxiters=cap)
+    chunk, geom = tl.initialiseapp(s(), backend=_device())
+    assert chunk.get_option("ring_stages_effective") == 4
+    assert chunk.get_option("rows_per_chunk") > 8                      # the clamp bites
+    assert chunk.get_option("fused_grid") <= chunk.get_option("max_grid")
+    assert chunk.get_option("pw_grid") <= chunk.get_option("max_grid")
+    st = s()
+    recs, final = tl.diffuse(chunk, st, geom)
+    o, og = tl.initialiseapp(s(), backend=omp_oracle())
+    orecs, ofinal = tl.diffuse(o, s(), og)
+    assert recs[0]["iters"] == orecs[0]["iters"] == cap
+    assert abs(recs[0]["error"] / orecs[0]["error"] - 1) < 1e-9
+    for k in ("vol", "mass", "ie", "temp"):
+        assert abs(final[k] / ofinal[k] - 1) < 1e-10, k
+    for f in ("u", "energy", "p", "r", "w"):          # 30 iterations in, the work vectors are still large: each on its own scale
+        a, b = chunk.get_field(f), o.get_field(f)
+        assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max(), f
+        del a, b
+    chunk.close(); o.close()
+
+
+@pytest.mark.timeout(1200)
+def test_wide_strip_grid_clamp_matches_oracle():
+    """16384 columns (256 strips, as in the 16384^2 tiles): with 2048 rows the grid bound clamps both tilings."""
+    nx, ny, cap = 16384, 2048, 36
+    # errorswitch with a huge epslim: leave CG after CGEIGENITERS = 20 iterations (Cheby.jl:25-27), so that the
+    # Chebyshev / PPCG kernels get 16 iterations inside the cap
+    sw = {"errorswitch": True, "epslim": 1e30}
+    for solver, over in (("cg", {}), ("ppcg", {"ppcginnersteps": 4, **sw}), ("cheby", sw)):
+        s = lambda: classic_settings(nx, ny=ny, steps=1, solver=solver, maxiters=cap, **over)
+        chunk, geom = tl.initialiseapp(s(), backend=_device())
+        assert chunk.get_option("rows_per_chunk") > 8 and chunk.get_option("fused_grid") <= chunk.get_option("max_grid")
+        assert chunk.get_option("pair_grid") <= chunk.get_option("max_grid")
+        recs, final = tl.diffuse(chunk, s(), geom)
+        o, og = tl.initialiseapp(s(), backend=omp_oracle())
+        orecs, ofinal = tl.diffuse(o, s(), og)
+        assert recs[0]["iters"] == orecs[0]["iters"] == cap, (solver, recs, orecs)
+        assert recs[0]["cg_iters"] == orecs[0]["cg_iters"] == (cap if solver == "cg" else 20)
+        assert abs(final["temp"] / ofinal["temp"] - 1) < 1e-10
+        assert rel(chunk.get_field("u"), o.get_field("u")) < 1e-9, solver
+        chunk.close(); o.close()
+
+
+# ---- full-size properties at 8192^2 (BASELINE configs[3] size): the oracle would take minutes ------
+def _properties(chunk, hd=2):
+    """Size-independent facts of the implicit step A u = u0 (A symmetric with unit row sums, reflective sides):
+    sum(r_true) = sum(u0) - sum(u) exactly, so energy is conserved to the residual; u stays positive; the halo of
+    u reflects its interior (haloupdate!).  Returns max |r_true| (residual! ran in solvefinished!)."""
+    u = chunk.get_field("u")
+    u0 = chunk.get_field("u0")
+    r = chunk.get_field("r")
+    ui, u0i, ri = u[hd:-hd, hd:-hd], u0[hd:-hd, hd:-hd], r[hd:-hd, hd:-hd]
+    assert abs((u0i.sum() - ui.sum()) - ri.sum()) <= 1e-11 * abs(u0i.sum())
+    assert ui.min() > 0
+    np.testing.assert_array_equal(u[hd - 1, hd:-hd], u[hd, hd:-hd])      # reflected halos (haloupdate! u)
+    np.testing.assert_array_equal(u[hd:-hd, -hd], u[hd:-hd, -hd - 1])
+    np.testing.assert_array_equal(u[hd:-hd, hd - 1], u[hd:-hd, hd])
+    return float(np.abs(ri).max()), float(abs(ui.sum() / u0i.sum() - 1))
+
+
+@pytest.mark.timeout(1800)
+def test_full_size_8192_cg_properties():
+    """8192^2 CG to convergence (more than the deck's 10000 iterations: ~1.2 N)."""
+    s = classic_settings(8192, steps=1, solver="cg", checkresult=True, maxiters=20000)
+    chunk, geom = tl.initialiseapp(s, backend=_device())
+    assert chunk.get_option("ring_stages_effective") == 4 and chunk.get_option("rows_per_chunk") > 8
+    recs, final = tl.diffuse(chunk, s, geom)
+    assert 8000 < recs[0]["iters"] < 14000, recs
+    assert np.sqrt(abs(recs[0]["error"])) < 1e-15
+    assert recs[0]["kernel_launches"] >= 2 * recs[0]["iters"]
+    rmax, drift = _properties(chunk)
+    assert rmax < 1e-9 and drift < 1e-11, (rmax, drift)
+    chunk.close()
+
+
+@pytest.mark.timeout(1800)
+def test_full_size_8192_ppcg_properties():
+    """BASELINE configs[3]: 8192^2 PPCG, 10 inner steps (pair kernels on, ring depth 4), capped at 2600 iterations
+    as in the benchmark leg (the algorithm the reference states converges slowly at this size: PPCG.jl:88-92 builds
+    p from the smoothed r).  Pair and one-step-per-kernel runs must agree."""
+    out = {}
+    for pair in (1, 0):
+        s = classic_settings(8192, steps=1, solver="ppcg", checkresult=True, maxiters=2600)
+        chunk, geom = tl.initialiseapp(s, backend=_device())
+        chunk.set_option("ppcg_pair", pair)
+        assert chunk.get_option("ring_stages_effective") == 4
+        recs, final = tl.diffuse(chunk, s, geom)
+        r = recs[0]
+        assert r["iters"] == 2600 and r["cg_iters"] > 30 and r["inner_total"] == 10 * r["cheby_iters"] > 0, r
+        per_outer = 2 + (5 if pair else 10)
+        assert r["kernel_launches"] < 2 * r["cg_iters"] + per_outer * (r["cheby_iters"] + 8) + 400, r
+        _properties(chunk)
+        out[pair] = (r, chunk.get_field("u"), final["temp"])
+        chunk.close()
+    (ra, ua, ta), (rb, ub, tb) = out[1], out[0]
+    assert (ra["iters"], ra["cg_iters"], ra["cheby_iters"]) == (rb["iters"], rb["cg_iters"], rb["cheby_iters"])
+    assert abs(ra["error"] / rb["error"] - 1) < 1e-6
+    assert rel(ua, ub) < 1e-10 and abs(ta / tb - 1) < 1e-12

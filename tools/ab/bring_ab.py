@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')
 import tealeaf_jl_b200 as tl
-from conftest import classic_settings
+from tealeaf_jl_b200.decks import classic_settings
 from tealeaf_jl_b200.device import DeviceChunk
 for N in (4096, 8192, 2048, 1024, 256):
     iters = 2000 if N <= 1024 else (600 if N <= 4096 else 300)

@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')
 import tealeaf_jl_b200 as tl
-from conftest import classic_settings
+from tealeaf_jl_b200.decks import classic_settings
 from tealeaf_jl_b200.device import DeviceChunk
 sizes = [int(a) for a in sys.argv[1:]] or [256, 1024, 2048, 4096, 8192]
 for N in sizes:

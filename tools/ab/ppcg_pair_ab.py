@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')
 import tealeaf_jl_b200 as tl
-from conftest import classic_settings
+from tealeaf_jl_b200.decks import classic_settings
 from tealeaf_jl_b200.device import DeviceChunk
 from tealeaf_jl_b200.solvers import get_solver
 for N, iters in ((8192, 0), (2048, 0)):

@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')
 import tealeaf_jl_b200 as tl
-from conftest import classic_settings
+from tealeaf_jl_b200.decks import classic_settings
 from tealeaf_jl_b200.device import DeviceChunk
 shapes = [(2048, 1024), (2048, 2048), (4096, 2048), (1024, 1024), (1024, 512)]
 for nx, ny in shapes:

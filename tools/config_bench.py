@@ -46,7 +46,7 @@ def main():
     from tealeaf_jl_b200.chunk import HostGeometry
     from tealeaf_jl_b200.device import DeviceChunk
     from tealeaf_jl_b200.solvers import get_solver
-    from conftest import classic_settings
+    from tealeaf_jl_b200.decks import classic_settings
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 import tealeaf_jl_b200 as tl  # noqa: E402
-from conftest import classic_settings  # noqa: E402
+from tealeaf_jl_b200.decks import classic_settings
 from tealeaf_jl_b200.device import DeviceChunk  # noqa: E402
 
 CASES = [("cg", 97, 61, {}, {}), ("cg", 130, 40, {}, {"cg_persist": 1}), ("cg", 75, 90, {}, {"b_ring": 6}),
