@@ -43,6 +43,17 @@ KERNEL_A_PHYS_BYTES = 64    # what it physically moves: read r,p,u,kx,ky; write 
 KERNEL_B_ALG_BYTES = 24     # k_cg_fused_r: the r half of ur!
 
 
+def _load_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
+TRAFFIC = _load_traffic()     # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed kernel@NXxNY
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -195,6 +206,110 @@ def workload_name(ngpus):
 
 
 # ------------------------------------------------------------------------------------------
+# BASELINE.json configs[2] / configs[3] on the N GPUs (strong scaling) and the weak-scaling base tile
+# ------------------------------------------------------------------------------------------
+def other_config_legs(world, rank, local_rank, dist, peak, maxr, budget_s=75.0):
+    """One bounded solve per configuration, timed on the device (CUDA events on the solve stream, max over
+    ranks); the CG presteps and the Chebyshev / PPCG phase are timed separately (tl_get_option
+    "last_cg_phase_ms").  Iteration caps make the legs finish in seconds: both solvers stop on maxiters,
+    the per-iteration figures do not depend on it."""
+    import tealeaf_jl_b200 as tl
+    from tealeaf_jl_b200 import dist as tld
+    from tealeaf_jl_b200.device import DeviceChunk
+    from tealeaf_jl_b200.solvers import get_solver
+    t_begin = time.perf_counter()
+
+    def solve_leg(solver, nx, ny, maxiters, over=None, options=None, tile_per_gpu=False):
+        s = classic(nx, ny, 1, maxiters=maxiters, solver=solver)
+        for k, v in (over or {}).items():
+            setattr(s, k, v)
+        if world > 1 and not tile_per_gpu:
+            chunk, geom, _ = tld.create_tile(s, dist, local_rank, options=options)
+        else:
+            chunk, geom = tl.initialiseapp(s, backend=DeviceChunk, device=local_rank)
+            for k, v in (options or {}).items():
+                chunk.set_option(k, v)
+        rx, ry = s.dtinit / s.dx ** 2, s.dtinit / s.dy ** 2
+        best = None
+        for _ in range(2):                       # the first pass builds the graphs
+            chunk.copy_field("energy", "energy0")
+            tl.haloupdate(chunk, s, 1, ["energy", "density"])
+            info = get_solver(solver).solve(chunk, s, rx, ry)
+            info["cg_ms"] = chunk.get_option("last_cg_phase_ms")
+            if best is None or info["solve_ms"] < best["solve_ms"]:
+                best = info
+        chunk.close()
+        ms, cg_ms = maxr(best["solve_ms"]), maxr(best["cg_ms"])
+        cells = nx * ny
+        ngpu = 1 if tile_per_gpu else world
+        out = {"global_cells": [nx, ny], "n_gpus": ngpu, "options": options or {}, "max_iters": maxiters,
+               "iters": best["iters"], "cg_iters": best["cg_iters"], "solve_ms": ms, "cg_phase_ms": cg_ms,
+               "error": best["error"], "kernel_launches": best["kernel_launches"]}
+        if solver == "cg":
+            sweeps, alg = best["iters"], 104 * best["iters"]
+            out.update(us_per_iteration=1e3 * ms / max(best["iters"], 1))
+        elif solver == "cheby":
+            ch = best["cheby_iters"]
+            sweeps, alg = best["iters"], 104 * best["cg_iters"] + 88 * ch
+            ph = max(ms - cg_ms, 1e-9)
+            out.update(cheby_iters=ch, cheby_phase_ms=ph, us_per_cheby_iteration=1e3 * ph / max(ch, 1),
+                       cheby_cell_iterations_per_s=cells * ch / (ph * 1e-3),
+                       cheby_algorithmic_gbs_per_gpu=88 * cells * ch / (ph * 1e-3) / 1e9 / ngpu,
+                       cheby_frac_of_measured_peak=88 * cells * ch / (ph * 1e-3) / 1e9 / ngpu / peak)
+        else:
+            outer, inner = best["cheby_iters"], best["inner_total"]
+            sweeps, alg = best["cg_iters"] + outer + inner, 104 * best["cg_iters"] + 128 * outer + 80 * inner
+            ph = max(ms - cg_ms, 1e-9)
+            out.update(outer_iters=outer, inner_steps_total=inner, halo_depth_k=best.get("halo_depth_k"), ppcg_phase_ms=ph,
+                       us_per_inner_step_incl_outer=1e3 * ph / max(inner, 1), us_per_sweep=1e3 * ph / max(outer + inner, 1),
+                       ppcg_cell_sweeps_per_s=cells * (outer + inner) / (ph * 1e-3),
+                       ppcg_algorithmic_gbs_per_gpu=(128 * outer + 80 * inner) * cells / (ph * 1e-3) / 1e9 / ngpu,
+                       ppcg_frac_of_measured_peak=(128 * outer + 80 * inner) * cells / (ph * 1e-3) / 1e9 / ngpu / peak)
+        out.update(cell_iterations_per_s=cells * sweeps / (ms * 1e-3),
+                   algorithmic_gbs_per_gpu=alg * cells / (ms * 1e-3) / 1e9 / ngpu,
+                   frac_of_measured_peak=alg * cells / (ms * 1e-3) / 1e9 / ngpu / peak)
+        return out
+
+    legs = {"note": "BASELINE.json configs[2] (Chebyshev 4096^2 global) and configs[3] (PPCG 8192^2 global, 10 inner steps) solved on "
+                    "the N GPUs of this run (strong scaling), iteration-capped, device-timed, max over ranks; algorithmic bytes per "
+                    "cell: CG 104, Chebyshev 88, PPCG 128 per outer + 80 per inner step (SURVEY.md section 8d); fractions are of the "
+                    "measured copy bandwidth per GPU.  default = two iterations / inner steps per pass (on tiles: one exchange per two)"}
+    plan = [("chebyshev_4096", "cheby", 4096, 4096, 2600, None, None),
+            ("ppcg_8192", "ppcg", 8192, 8192, 2600, None, None),
+            ("chebyshev_4096_one_per_pass", "cheby", 4096, 4096, 2600, None, {"cheby_pair": 0}),
+            ("ppcg_8192_one_per_pass_exchange_every_step", "ppcg", 8192, 8192, 2600, {"ppcghalodepth": 1}, {"ppcg_pair": 0})]
+    if world > 1:
+        plan.append(("ppcg_8192_one_per_pass_exchange_every_halo_depth", "ppcg", 8192, 8192, 2600, {"ppcghalodepth": 2}, {"ppcg_pair": 0}))
+        plan.append(("cg_4096_strong", "cg", 4096, 4096, 1500, None, None))
+    for name, solver, nx, ny, cap, over, opts in plan:
+        # every rank must take the same decision: rank 0's clock decides
+        go = 1.0 if time.perf_counter() - t_begin < budget_s else 0.0
+        if dist is not None:
+            import torch
+            t = torch.tensor([go], dtype=torch.float64, device="cuda")
+            dist.broadcast(t, 0)
+            go = float(t.item())
+        if not go:
+            legs[name] = {"skipped": "time budget of the side legs spent"}
+            continue
+        try:
+            legs[name] = solve_leg(solver, nx, ny, cap, over, opts)
+        except Exception as e:       # a side leg must never break the headline line
+            legs[name] = {"error": repr(e)[:300]}
+            if dist is not None:
+                break                # the ranks may no longer be in step
+    if world == 1:
+        try:
+            legs["weak_tile_16384"] = dict(solve_leg("cg", 16384, 16384, 200, None, None, tile_per_gpu=True),
+                                           note="the N > 1 workload's tile (16384^2 cells, CG capped at 200 iterations) solved alone: "
+                                                "weak-scaling efficiency at N GPUs = value_N / (N x this cell_iterations_per_s)")
+        except Exception as e:
+            legs["weak_tile_16384"] = {"error": repr(e)[:300]}
+    legs["seconds"] = time.perf_counter() - t_begin
+    return legs
+
+
+# ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -334,12 +449,7 @@ def run_b200(args):
     ka_ms = chunk.time_kernel("cg_fused_w", 30)
     kb_ms = chunk.time_kernel("cg_fused_r", 30)
     it_ms = solve_ms / max(iters, 1)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(f"k_cg_fused_w@{tile_nx}x{tile_ny}")
-    except Exception:
-        pass
+    traffic = TRAFFIC.get(f"k_cg_fused_w@{tile_nx}x{tile_ny}")      # ncu dram bytes per launch at this tile size, or None
     roofline = {
         "bound": "hbm", "kernel": "k_cg_fused_w_ring<true, S, MINB> (CG kernel A)",
         "achieved": KERNEL_A_ALG_BYTES * tile_cells / (ka_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -356,7 +466,7 @@ def run_b200(args):
     }
 
     # ---- the reduction-free iterations of configs[2] / configs[3] on the same tile (kernels timed alone) ----
-    other = None
+    kernels_alone = None
     if world == 1:
         try:
             def per_it(name, its_per_launch):
@@ -364,26 +474,39 @@ def run_b200(args):
                 return 1e3 * ms / its_per_launch
             c1, c2 = per_it("cheby_fused", 1), per_it("cheby_pair", 2)
             p1, p2 = per_it("ppcg_inner", 1), per_it("ppcg_pair", 2)
-            other = {
-                "note": "kernels of BASELINE.json configs[2]/[3] timed alone on this 4096x4096 tile (CUDA events, 30 launches); "
-                        "two_per_pass = temporal blocking (k_cheby_pair_ring / k_ppcg_pair_ring), the default on a single tile",
+            tj = TRAFFIC.get
+            kernels_alone = {
+                "note": "kernels of configs[2]/[3] timed alone on this 4096x4096 tile (CUDA events, 30 launches); two_per_pass = "
+                        "temporal blocking (k_cheby_pair_ring / k_ppcg_pair_ring); physical_bytes_per_cell_pass = ncu dram bytes",
                 "chebyshev_iteration": {"one_per_pass_us": c1, "two_per_pass_us": c2, "algorithmic_bytes_per_cell": 88,
                                         "cell_iterations_per_s": tile_cells / (c2 * 1e-6),
-                                        "algorithmic_gbs": 88 * tile_cells / (c2 * 1e-6) / 1e9},
+                                        "algorithmic_gbs": 88 * tile_cells / (c2 * 1e-6) / 1e9,
+                                        "dram_bytes_per_launch_two_per_pass": tj("k_cheby_pair_ring@4096x4096"),
+                                        "physical_gbs": (tj("k_cheby_pair_ring@4096x4096") or 0) / (2 * c2 * 1e-6) / 1e9},
                 "ppcg_inner_step": {"one_per_pass_us": p1, "two_per_pass_us": p2, "algorithmic_bytes_per_cell": 80,
                                     "cell_steps_per_s": tile_cells / (p2 * 1e-6),
-                                    "algorithmic_gbs": 80 * tile_cells / (p2 * 1e-6) / 1e9},
+                                    "algorithmic_gbs": 80 * tile_cells / (p2 * 1e-6) / 1e9,
+                                    "dram_bytes_per_launch_two_per_pass": tj("k_ppcg_pair_ring@4096x4096"),
+                                    "physical_gbs": (tj("k_ppcg_pair_ring@4096x4096") or 0) / (2 * p2 * 1e-6) / 1e9},
             }
         except Exception as e:      # never let the side measurement break the headline line
-            other = {"error": repr(e)}
+            kernels_alone = {"error": repr(e)}
+    chunk.close()
+    chunk = None
+    other = other_config_legs(world, rank, local_rank, dist, peak, maxr) if not args.no_legs else None
+    if other is not None and kernels_alone is not None:
+        other["kernels_alone_4096"] = kernels_alone
 
-    cpu = None
+    cpu = cpu_serial = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle.oracle import load
         threads = load().tlo_max_threads()
         v, secs = cpu_cg_sample(4096, 600, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"600 CG iterations of the same 4096x4096 deck ({secs:.1f} s), OpenMP oracle"}
+        v1, secs1 = cpu_cg_sample(4096, 40, 1)      # what the reference is: serial (no threading anywhere, CG.jl:82-90)
+        cpu_serial = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                      "sample": f"40 CG iterations of the same deck on one thread ({secs1:.1f} s)"}
     elif rank == 0:
         cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "N>1: measured at N=1 only"}
 
@@ -403,6 +526,7 @@ def run_b200(args):
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "solve_only_ms_per_step": solve_ms / args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
+            **({"cpu_baseline_serial": cpu_serial} if cpu_serial else {}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * field_bytes,
                     "d2h_bytes_per_step": field_bytes + 32, "ms_per_step": 1e3 * e2e_wall / args.steps,
                     "host_numa_binding": numa},
@@ -412,7 +536,6 @@ def run_b200(args):
                 "this rank's tile solved alone (1x1, 60 CG iterations incl. init) in the same job; "
                 "weak-scaling efficiency of the N-GPU workload = value / (N x this)"}} if solo else {}),
         }))
-    chunk.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -426,15 +549,19 @@ def main():
     ap.add_argument("--tile", type=int, default=16384, help="N>1: cells per GPU per side")
     ap.add_argument("--cap-iters", type=int, default=200, help="N>1: CG iterations per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-legs", action="store_true", help="skip other_configs (configs[2]/[3] and the weak base tile)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    import __graft_entry__
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        __graft_entry__.build()
     if args.impl == "reference":
+        from oracle import oracle as _o      # the CPU arm never builds or loads the CUDA library
+        if int(os.environ.get("RANK", "0")) == 0:
+            _o.build()
         run_reference(args)
     else:
+        import __graft_entry__
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            __graft_entry__.build()
         run_b200(args)
 
 

@@ -9,7 +9,12 @@
  *
  * The deck is the classic 5-state TeaLeaf benchmark deck on [0,10]^2.
  *
- *   tea_c_host <x_cells> <y_cells> <end_step> <cg|cheby|ppcg|jacobi> [max_iters] [ppcg_inner_steps]
+ *   tea_c_host [--gpus N] [--share-gpu] <x_cells> <y_cells> <end_step> <cg|cheby|ppcg|jacobi> [max_iters] [ppcg_inner_steps]
+ *
+ * --gpus N: ONE context for the whole mesh spread over N GPUs of this process (tl_create_multi): the loop below is
+ * unchanged -- the reference has one process and one Chunk (run.jl:45-47).  --share-gpu puts all N tiles on device 0
+ * (a test mode for single-GPU boxes; needs CUDA_MODULE_LOADING=EAGER in the environment).  With --gpus the final u
+ * field is downloaded through the global tl_get_field and its interior sum is printed as "usum <s>".
  *
  * Output: one line per timestep  "step <tt> iters <n> error <rr>"  and a final
  * "summary vol <v> mass <m> ie <e> temp <t>"  (%.17g, i.e. round-trip exact).
@@ -32,8 +37,14 @@
   } while (0)
 
 int main(int argc, char **argv) {
+  int ngpus = 0, share_gpu = 0;
+  while (argc > 1 && argv[1][0] == '-') {
+    if (strcmp(argv[1], "--gpus") == 0 && argc > 2) { ngpus = atoi(argv[2]); argv += 2; argc -= 2; }
+    else if (strcmp(argv[1], "--share-gpu") == 0) { share_gpu = 1; argv += 1; argc -= 1; }
+    else break;
+  }
   if (argc < 5) {
-    fprintf(stderr, "usage: %s x_cells y_cells end_step cg|cheby|ppcg|jacobi [max_iters] [ppcg_inner_steps]\n", argv[0]);
+    fprintf(stderr, "usage: %s [--gpus N] [--share-gpu] x_cells y_cells end_step cg|cheby|ppcg|jacobi [max_iters] [ppcg_inner_steps]\n", argv[0]);
     return 2;
   }
   const int nx = atoi(argv[1]), ny = atoi(argv[2]), end_step = atoi(argv[3]);
@@ -69,13 +80,19 @@ int main(int argc, char **argv) {
   }
 
   tl_ctx *ctx = NULL;
-  int rc = tl_create(&ctx, nx, ny, halo_depth, max_iters, 0);     /* Chunk(settings), chunk.jl:68-89 */
+  int rc;
+  if (ngpus > 0) {                                                /* one Chunk over N GPUs */
+    int devices[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    rc = tl_create_multi(&ctx, nx, ny, halo_depth, max_iters, ngpus, share_gpu ? devices : NULL, 0, 0);
+  } else {
+    rc = tl_create(&ctx, nx, ny, halo_depth, max_iters, 0);       /* Chunk(settings), chunk.jl:68-89 */
+  }
   if (rc == TL_ERR_NO_DEVICE) {
     fprintf(stderr, "tl_create: no sm_100 device (TL_ERR_NO_DEVICE); libtealeaf_b200 has no CPU fallback\n");
     return 3;
   }
   if (rc != TL_OK) {
-    fprintf(stderr, "tl_create failed (%d)\n", rc);
+    fprintf(stderr, "tl_create failed (%d): %s\n", rc, tl_last_error(NULL));
     return 1;
   }
   if (tl_abi_version() != TL_ABI_VERSION) {
@@ -118,6 +135,18 @@ int main(int argc, char **argv) {
     double vol, mass, ie, temp;
     CHECK(tl_field_summary(ctx, dx * dy, &vol, &mass, &ie, &temp));                               /* :82 */
     printf("summary vol %.17g mass %.17g ie %.17g temp %.17g\n", vol, mass, ie, temp);
+  }
+  if (ngpus > 0) {   /* the global gather: chunk.u as the reference holds it, (x, y) column-major with halos */
+    const long x = nx + 2 * halo_depth, y = ny + 2 * halo_depth;
+    double *u = (double *)malloc((size_t)(x * y) * sizeof(double));
+    double usum = 0.0;
+    long i, j;
+    if (!u) { tl_destroy(ctx); return 1; }
+    CHECK(tl_get_field(ctx, TL_U, u, x));
+    for (j = halo_depth; j < y - halo_depth; j++)
+      for (i = halo_depth; i < x - halo_depth; i++) usum += u[j * x + i];
+    printf("usum %.17g\n", usum);
+    free(u);
   }
   tl_destroy(ctx);
   return 0;

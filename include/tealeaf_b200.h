@@ -20,8 +20,9 @@
  *    halos, x = xcells + 2*halo_depth contiguous (src/chunk.jl:68-70); element [kk,jj]
  *    (1-based) is host[(kk-1) + (jj-1)*ld].
  *  - one caller thread per context (the reference is single-threaded).
- *  - one context == one GPU == one tile of the px x py decomposition (one process per
- *    GPU; see tl_comm_*).  A single-GPU run is the 1x1 case.
+ *  - tl_create: one context == one GPU (the 1x1 case).  Several GPUs: either ONE context for the whole
+ *    mesh in one process (tl_create_multi -- what a host with a single Chunk like the reference's
+ *    needs), or one context per tile with one process per GPU (tl_create_tile + tl_comm_*).
  */
 #ifndef TEALEAF_B200_H
 #define TEALEAF_B200_H
@@ -77,7 +78,19 @@ int tl_create(tl_ctx **out, int xcells, int ycells, int halo_depth, int max_iter
  * another tile are exchanged, the others are reflective (src/kernels.jl:191-210). */
 int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_depth, int max_iters, int device,
                    int rank, int px, int py);
+/* ONE context spanning `ngpus` GPUs of THIS process: the reference is one process with one Chunk (run.jl:45-47,
+ * src/TeaLeaf.jl:35-44), so its host gets one handle for the GLOBAL xcells x ycells mesh and every entry point of this
+ * header works on it unchanged -- tl_set_field / tl_get_field scatter / gather the reference's global (x, y) matrices
+ * over the px x py tiles (halos included), tl_paint_states paints every tile at its offset, every kernel / solve call
+ * runs on all tiles at once (they exchange halos and dot products over NVLink inside the kernels) and returns the
+ * all-tiles scalars.  devices: `ngpus` CUDA device indices (NULL: 0 .. ngpus-1; repeating an index puts several tiles
+ * on one GPU -- a test mode that needs CUDA_MODULE_LOADING=EAGER); px, py: the decomposition (<= 0: 1x2, 2x2, 2x4, ...:
+ * y, the strided dimension, is split first).  The caller stays single-threaded; the library runs one service thread
+ * per tile.  tl_comm_* must not be called on such a context. */
+int tl_create_multi(tl_ctx **out, int xcells, int ycells, int halo_depth, int max_iters, int ngpus,
+                    const int *devices, int px, int py);
 void tl_destroy(tl_ctx *ctx);
+/* ctx == NULL: why the last tl_create / tl_create_tile / tl_create_multi of this process failed */
 const char *tl_last_error(const tl_ctx *ctx);
 int tl_abi_version(void);
 /* Tuning / A-B knobs.  None of them changes per-cell arithmetic; those that change how the tile is cut into

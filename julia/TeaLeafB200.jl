@@ -50,15 +50,25 @@ function check(chunk::B200Chunk, rc::Cint)
 end
 
 """
-    B200Chunk(settings; device = 0)
+    B200Chunk(settings; device = 0, ngpus = 1, devices = nothing, px = 0, py = 0)
 
-`Chunk(settings)` (src/chunk.jl:68-89) on the GPU.
+`Chunk(settings)` (src/chunk.jl:68-89) on the GPU.  `ngpus > 1` spreads the ONE chunk over that many GPUs of this
+process (`tl_create_multi`): every method below works on it unchanged, `upload!` / `download` scatter / gather the
+global matrices.  The reference stays one process with one `Chunk` (run.jl:45-47).
 """
-function B200Chunk(set::Settings; device::Int = 0)
+function B200Chunk(set::Settings; device::Int = 0, ngpus::Int = 1, devices = nothing, px::Int = 0, py::Int = 0)
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
-    rc = ccall((:tl_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint),
-               ctx, set.xcells, set.ycells, set.halodepth, set.maxiters, device)
-    rc == 0 || throw("tl_create failed ($(rc)): a B200 (sm_100) GPU is required, there is no CPU fallback")
+    rc = if ngpus > 1
+        devs = devices === nothing ? Ptr{Cint}(C_NULL) : convert(Vector{Cint}, devices)
+        GC.@preserve devs ccall((:tl_create_multi, LIB), Cint,
+                                (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint, Ptr{Cint}, Cint, Cint),
+                                ctx, set.xcells, set.ycells, set.halodepth, set.maxiters, ngpus, devs, px, py)
+    else
+        ccall((:tl_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cint),
+              ctx, set.xcells, set.ycells, set.halodepth, set.maxiters, device)
+    end
+    rc == 0 || throw("tl_create failed ($(rc)): " * unsafe_string(ccall((:tl_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)) *
+                     " -- a B200 (sm_100) GPU is required, there is no CPU fallback")
     chunk = B200Chunk(ctx[], set.xcells + 2set.halodepth, set.ycells + 2set.halodepth, set.halodepth,
                       set.dx * set.dy, zeros(set.maxiters), zeros(set.maxiters), 0.0, 0.0)
     finalizer(c -> ccall((:tl_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.ctx), chunk)
@@ -261,8 +271,8 @@ device from `settings.states` (`tl_paint_states`, bit-identical to the host pain
 of `initialiseapp!` (halo priming, `energy .= energy0`) runs on the device as well.  (A host that
 prefers the reference's own painter calls `upload!` with `host.density`, `host.energy0`, `host.u`.)
 """
-function initialiseapp!(settings::Settings; device::Int = 0)::B200Chunk
-    chunk = B200Chunk(settings; device = device)
+function initialiseapp!(settings::Settings; device::Int = 0, ngpus::Int = 1)::B200Chunk
+    chunk = B200Chunk(settings; device = device, ngpus = ngpus)
     TeaLeaf.setchunkstate!(chunk, settings)   # not exported by the reference (src/chunk.jl:4-7): qualified
     TeaLeaf.Kernels.haloupdate!(chunk, settings, 1, [:density, :energy0, :energy])
     check(chunk, ccall((:tl_copy_field, LIB), Cint, (Ptr{Cvoid}, Cint, Cint), chunk.ctx, FIELD_ID[:energy], FIELD_ID[:energy0]))

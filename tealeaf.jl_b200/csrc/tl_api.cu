@@ -73,7 +73,10 @@ struct CommBlob {  // what tl_comm_export hands to the other ranks
   unsigned long long slab_ptr;    // (CUDA-IPC handles cannot be opened by the process that made them)
 };
 
+struct Multi;   // tl_multi.inl: a context that spans several GPUs of this process
+
 struct tl_ctx {
+  Multi *multi = nullptr;   // non-null: this context is the single-Chunk face of px x py tile contexts (tl_create_multi)
   Geo g{};
   int max_iters = 0, device = 0;
   int rank = 0, px = 1, py = 1, cx = 0, cy = 0, nranks = 1;
@@ -116,9 +119,9 @@ struct tl_ctx {
   bool comm_ready = false;
   int use_pdl = 0;          // programmatic dependent launch between the kernels of the iteration loops: measured
                             // SLOWER (profiles/r01d_pdl_sweep.log: 1024^2 CG 24.7 -> 27.6 us/iteration), kept as an option
-  int pair_tiled = 0;       // EXPERIMENTAL (not yet run on a GPU): Chebyshev pairs on tiles, one rendezvous per two iterations
-  int ppcg_pair = 1;        // 1: single tile, even inner_steps -- PPCG inner steps run two per pass (k_ppcg_pair_ring)
-  int cheby_pair = 1;       // 1: single tile -- reduction-free Chebyshev iterations run two per pass (k_cheby_pair_ring)
+  int pair_tiled = 1;       // 1: the pair kernels also run on tiles (depth-2 halos, one rendezvous per two iterations / inner steps)
+  int ppcg_pair = 1;        // 1: PPCG inner steps run two per pass (k_ppcg_pair_ring; an odd count ends with one single step)
+  int cheby_pair = 1;       // 1: reduction-free Chebyshev iterations run two per pass (k_cheby_pair_ring)
   int pair_rows = 32;       // rows per warp task of the pair kernel (two redundant rows per task)
   Tiling pair_tiling{};
   int pair_grid = 0;
@@ -328,11 +331,25 @@ static void destroy_graphs(tl_ctx *c) {
   if (c->g_jacobi) { cudaGraphExecDestroy(c->g_jacobi); c->g_jacobi = nullptr; }
 }
 
+
+// ---- multi-GPU-in-one-process contexts (tl_multi.inl): every entry point forwards to the tiles ----
+template <typename F> static int multi_all(tl_ctx *c, F fn);                         // fn(tile, idx) on every tile, concurrently
+template <typename F> static int multi_scalar(tl_ctx *c, double *out, F fn);         // fn(tile, &v): the all-tiles value
+template <typename F> static int multi_max(tl_ctx *c, double *out, F fn);            // fn(tile, &v): max over tiles
+template <typename F> static int multi_solve(tl_ctx *c, tl_solve_info *info, F fn);  // fn(tile, &info, idx)
+static void multi_destroy(tl_ctx *c);
+static int multi_set_field(tl_ctx *c, int field, const double *host, long ld);
+static int multi_get_field(tl_ctx *c, int field, double *host, long ld);
+static int multi_field_summary(tl_ctx *c, double cell_volume, double *vol, double *mass, double *ie, double *temp);
+static int multi_launch_count(tl_ctx *c, long long *count);
+static int multi_tile_offset(const tl_ctx *c, int idx, int *x0, int *y0);
+#define TL_IS_MULTI(c) ((c) && (c)->multi)
+
 extern "C" int tl_abi_version(void) { return TL_ABI_VERSION; }
 
-extern "C" const char *tl_last_error(const tl_ctx *c) { return c ? c->err.c_str() : "null context"; }
+static std::string g_create_error;   // why the last tl_create* call of the process failed (there is no context to ask then)
+extern "C" const char *tl_last_error(const tl_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
-static std::string g_create_error;
 extern "C" int tl_set_option(tl_ctx *c, const char *name, double value);
 extern "C" void tl_destroy(tl_ctx *c);
 
@@ -441,6 +458,7 @@ extern "C" int tl_create(tl_ctx **out, int xcells, int ycells, int halo_depth, i
 }
 
 extern "C" void tl_destroy(tl_ctx *c) {
+  if (TL_IS_MULTI(c)) { multi_destroy(c); return; }
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
@@ -465,6 +483,7 @@ extern "C" void tl_destroy(tl_ctx *c) {
 }
 
 extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_set_option(t, name, value); });
   if (!c || !name) return TL_ERR_ARG;
   const std::string n(name);
   if (n == "blocks_per_sm") c->blocks_per_sm = std::max(1, (int)value);
@@ -515,6 +534,7 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
 
 // Read-back of an option or of a derived quantity (what the tests assert the measured code paths on).
 extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
+  if (TL_IS_MULTI(c)) return multi_max(c, value, [&](tl_ctx *t, double *o) { return tl_get_option(t, name, o); });
   if (!c || !name || !value) return TL_ERR_ARG;
   const std::string n(name);
   double v;
@@ -563,6 +583,7 @@ extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
 extern "C" int tl_comm_blob_size(void) { return (int)sizeof(CommBlob); }
 
 extern "C" int tl_comm_export(tl_ctx *c, void *blob) {
+  if (TL_IS_MULTI(c)) return tl_fail(c, TL_ERR_STATE, "tl_comm_export: a tl_create_multi context wires its own tiles");
   if (!c || !blob) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   CommBlob b;
@@ -591,6 +612,7 @@ extern "C" int tl_comm_unique_id(void *id128) {
 }
 
 extern "C" int tl_comm_connect(tl_ctx *c, const void *all_blobs, const void *id128) {
+  if (TL_IS_MULTI(c)) return tl_fail(c, TL_ERR_STATE, "tl_comm_connect: a tl_create_multi context wires its own tiles");
   if (!c) return TL_ERR_ARG;
   if (c->nranks == 1) { c->comm_ready = true; return TL_OK; }
   if (!all_blobs) return tl_fail(c, TL_ERR_ARG, "tl_comm_connect: the tiles' blobs are required");
@@ -781,6 +803,7 @@ static int tile_barrier(tl_ctx *c) {
 // field transfer
 // ---------------------------------------------------------------------------------------
 extern "C" int tl_set_field(tl_ctx *c, int field, const double *host, long ld) {
+  if (TL_IS_MULTI(c)) return multi_set_field(c, field, host, ld);
   if (!c || !host || field < 0 || field >= TL_NUM_FIELDS) return tl_fail(c, TL_ERR_ARG, "tl_set_field: bad argument");
   const Geo &g = c->g;
   const int x = g.nx + 2 * g.hd, y = g.ny + 2 * g.hd;
@@ -793,6 +816,7 @@ extern "C" int tl_set_field(tl_ctx *c, int field, const double *host, long ld) {
 }
 
 extern "C" int tl_get_field(tl_ctx *c, int field, double *host, long ld) {
+  if (TL_IS_MULTI(c)) return multi_get_field(c, field, host, ld);
   if (!c || !host || field < 0 || field >= TL_NUM_FIELDS) return tl_fail(c, TL_ERR_ARG, "tl_get_field: bad argument");
   const Geo &g = c->g;
   const int x = g.nx + 2 * g.hd, y = g.ny + 2 * g.hd;
@@ -805,6 +829,7 @@ extern "C" int tl_get_field(tl_ctx *c, int field, double *host, long ld) {
 }
 
 extern "C" int tl_copy_field(tl_ctx *c, int dst_field, int src_field) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_copy_field(t, dst_field, src_field); });
   if (!c || dst_field < 0 || dst_field >= TL_NUM_FIELDS || src_field < 0 || src_field >= TL_NUM_FIELDS)
     return tl_fail(c, TL_ERR_ARG, "tl_copy_field: bad field");
   CU(c, cudaSetDevice(c->device));
@@ -819,6 +844,12 @@ extern "C" int tl_copy_field(tl_ctx *c, int dst_field, int src_field) {
 // setchunkstate! on the device (src/chunk.jl:122-151)
 extern "C" int tl_paint_states(tl_ctx *c, int nstates, const tl_state *states, double xmin, double ymin, double dx,
                                double dy, int x0, int y0) {
+  if (TL_IS_MULTI(c))
+    return multi_all(c, [&](tl_ctx *t, int i) {
+      int tx = 0, ty = 0;
+      multi_tile_offset(c, i, &tx, &ty);
+      return tl_paint_states(t, nstates, states, xmin, ymin, dx, dy, x0 + tx, y0 + ty);
+    });
   if (!c || !states || nstates < 1) return tl_fail(c, TL_ERR_ARG, "tl_paint_states: bad argument");
   if (nstates > TL_MAX_STATES) return tl_fail(c, TL_ERR_ARG, "tl_paint_states: more than %d states", TL_MAX_STATES);
   CU(c, cudaSetDevice(c->device));
@@ -866,6 +897,7 @@ static int halo_update_buf(tl_ctx *c, int bufidx, int depth) {
 }
 
 extern "C" int tl_halo_update(tl_ctx *c, unsigned field_mask, int depth) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_halo_update(t, field_mask, depth); });
   if (!c || depth < 1 || depth > c->g.hd) return tl_fail(c, TL_ERR_ARG, "tl_halo_update: depth must be in 1..halo_depth");
   CU(c, cudaSetDevice(c->device));
   TRY(tile_barrier(c));  // neighbours' interiors must be final before they are pulled
@@ -891,6 +923,7 @@ static int cg_init_async(tl_ctx *c, int coef, double rx, double ry) {
 }
 
 extern "C" int tl_cg_init(tl_ctx *c, int coef, double rx, double ry, double *rro) {
+  if (TL_IS_MULTI(c)) return multi_scalar(c, rro, [&](tl_ctx *t, double *o) { return tl_cg_init(t, coef, rx, ry, o); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   TRY(cg_init_async(c, coef, rx, ry));
@@ -901,6 +934,7 @@ extern "C" int tl_cg_init(tl_ctx *c, int coef, double rx, double ry, double *rro
 }
 
 extern "C" int tl_cg_calc_w(tl_ctx *c, double *pw) {
+  if (TL_IS_MULTI(c)) return multi_scalar(c, pw, [&](tl_ctx *t, double *o) { return tl_cg_calc_w(t, o); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   LAUNCH_BASIC(c, k_calc_w, c->g, field_ptr(c, TL_P), c->buf[TL_KX], c->buf[TL_KY], c->buf[TL_W], c->partials,
@@ -913,6 +947,7 @@ extern "C" int tl_cg_calc_w(tl_ctx *c, double *pw) {
 }
 
 extern "C" int tl_cg_calc_ur(tl_ctx *c, double alpha, double *rrn) {
+  if (TL_IS_MULTI(c)) return multi_scalar(c, rrn, [&](tl_ctx *t, double *o) { return tl_cg_calc_ur(t, alpha, o); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   LAUNCH_BASIC(c, k_calc_ur, c->g, alpha, field_ptr(c, TL_P), c->buf[TL_W], field_ptr(c, TL_U), c->buf[TL_R],
@@ -925,6 +960,7 @@ extern "C" int tl_cg_calc_ur(tl_ctx *c, double alpha, double *rrn) {
 }
 
 extern "C" int tl_cg_calc_p(tl_ctx *c, double beta) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_cg_calc_p(t, beta); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   LAUNCH_BASIC(c, k_calc_p, c->g, beta, c->buf[TL_R], field_ptr(c, TL_P));
@@ -933,6 +969,7 @@ extern "C" int tl_cg_calc_p(tl_ctx *c, double beta) {
 }
 
 extern "C" int tl_copy_u(tl_ctx *c) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_copy_u(t); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   LAUNCH_BASIC(c, k_copy, c->g, 0, field_ptr(c, TL_U), c->buf[TL_U0]);
@@ -945,6 +982,7 @@ static int residual_async(tl_ctx *c) {
   return TL_OK;
 }
 extern "C" int tl_calc_residual(tl_ctx *c) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_calc_residual(t); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   TRY(residual_async(c));
@@ -953,6 +991,7 @@ extern "C" int tl_calc_residual(tl_ctx *c) {
 }
 
 extern "C" int tl_finalise(tl_ctx *c) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_finalise(t); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   LAUNCH_BASIC(c, k_finalise, c->g, field_ptr(c, TL_U), c->buf[TL_DENSITY], c->buf[TL_ENERGY]);
@@ -961,6 +1000,7 @@ extern "C" int tl_finalise(tl_ctx *c) {
 }
 
 extern "C" int tl_solve_finished(tl_ctx *c, int check_result) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_solve_finished(t, check_result); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   if (check_result) TRY(residual_async(c));
@@ -974,6 +1014,7 @@ static int norm2_async(tl_ctx *c, int field, double *dev_out) {
   return allreduce(c, dev_out, 1);
 }
 extern "C" int tl_norm2(tl_ctx *c, int field, double *out) {
+  if (TL_IS_MULTI(c)) return multi_scalar(c, out, [&](tl_ctx *t, double *o) { return tl_norm2(t, field, o); });
   if (!c || field < 0 || field >= TL_NUM_FIELDS) return tl_fail(c, TL_ERR_ARG, "tl_norm2: bad field");
   CU(c, cudaSetDevice(c->device));
   TRY(norm2_async(c, field, &c->st->red_aux[0]));
@@ -984,6 +1025,7 @@ extern "C" int tl_norm2(tl_ctx *c, int field, double *out) {
 }
 
 extern "C" int tl_cheby_init(tl_ctx *c, double theta, double *bb) {
+  if (TL_IS_MULTI(c)) return multi_scalar(c, bb, [&](tl_ctx *t, double *o) { return tl_cheby_init(t, theta, o); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   TRY(norm2_async(c, TL_U0, &c->st->red_aux[0]));   // Cheby.jl:68
@@ -997,6 +1039,7 @@ extern "C" int tl_cheby_init(tl_ctx *c, double theta, double *bb) {
 }
 
 extern "C" int tl_cheby_iterate(tl_ctx *c, double alpha, double beta, int calc_2norm, double *error) {
+  if (TL_IS_MULTI(c)) return multi_scalar(c, error, [&](tl_ctx *t, double *o) { return tl_cheby_iterate(t, alpha, beta, calc_2norm, o); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   LAUNCH_BASIC(c, k_cheby_wrp, c->g, 0, 1.0, alpha, beta, field_ptr(c, TL_U), c->buf[TL_U0], c->buf[TL_KX],
@@ -1014,6 +1057,7 @@ extern "C" int tl_cheby_iterate(tl_ctx *c, double alpha, double beta, int calc_2
 }
 
 extern "C" int tl_ppcg_init_sd(tl_ctx *c, double theta) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_ppcg_init_sd(t, theta); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   LAUNCH_BASIC(c, k_ppcg_init_sd, c->g, theta, c->buf[TL_R], field_ptr(c, TL_SD));
@@ -1022,6 +1066,7 @@ extern "C" int tl_ppcg_init_sd(tl_ctx *c, double theta) {
 }
 
 extern "C" int tl_ppcg_inner(tl_ctx *c, const double *alphas, const double *betas, int nsteps) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_ppcg_inner(t, alphas, betas, nsteps); });
   if (!c || !alphas || !betas || nsteps < 0) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_inner: bad argument");
   CU(c, cudaSetDevice(c->device));
   for (int pp = 0; pp < nsteps; pp++) {
@@ -1034,6 +1079,7 @@ extern "C" int tl_ppcg_inner(tl_ctx *c, const double *alphas, const double *beta
 }
 
 extern "C" int tl_field_summary(tl_ctx *c, double cell_volume, double *vol, double *mass, double *ie, double *temp) {
+  if (TL_IS_MULTI(c)) return multi_field_summary(c, cell_volume, vol, mass, ie, temp);
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   LAUNCH_BASIC(c, k_field_summary, c->g, cell_volume, c->buf[TL_DENSITY], c->buf[TL_ENERGY0], field_ptr(c, TL_U),
@@ -1367,6 +1413,10 @@ static void finish_timing(tl_ctx *c, tl_solve_info *info, long long launches0) {
 
 extern "C" int tl_cg_solve(tl_ctx *c, int coef, double rx, double ry, double eps, int max_iters,
                            tl_solve_info *info, double *cg_alphas, double *cg_betas) {
+  if (TL_IS_MULTI(c))
+    return multi_solve(c, info, [&](tl_ctx *t, tl_solve_info *o, int i) {
+      return tl_cg_solve(t, coef, rx, ry, eps, max_iters, o, i == 0 ? cg_alphas : nullptr, i == 0 ? cg_betas : nullptr);
+    });
   if (!c || !info) return TL_ERR_ARG;
   memset(info, 0, sizeof *info);
   CU(c, cudaSetDevice(c->device));
@@ -1415,56 +1465,47 @@ static int enqueue_cheby_iteration(tl_ctx *c) {
   return TL_OK;
 }
 
-// Two Chebyshev iterations = one kernel (single tile, option cheby_pair; k_cheby_pair_ring).
-template <int S, int MINB>
-static int launch_cheby_pair_ring(tl_ctx *c, const ChebyParams &P) {
-  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static unsigned long long prepared = 0;
-  TRY(tl_prepare_smem(c, k_cheby_pair_ring<S, MINB>, smem, &prepared));
-  CU(c, tl_launch(c, k_cheby_pair_ring<S, MINB>, c->pair_grid, TL_FUSED_THREADS, smem, P));
-  return TL_OK;
-}
-static int enqueue_cheby_pair(tl_ctx *c) {
-  ChebyParams P = cheby_params(c);
-  P.t = c->pair_tiling;
-  TRY((launch_cheby_pair_ring<4, 2>(c, P)));
-  CHECK_LAUNCH(c);
-  c->launches++;
-  return TL_OK;
-}
-// EXPERIMENTAL: the pair kernel on tiles (option pair_tiled; k_cheby_pair_tiled_ring)
-static bool cheby_pairs_tiled(const tl_ctx *c) {
-  if (!(c->cheby_pair && c->pair_tiled && c->nranks > 1 && c->comm_fused && c->g.hd >= 2)) return false;
+// Can the pair kernels run on this context's tiles?  (depth-2 halos, every tile at least 2 x 2 cells, fused exchange)
+static bool pairs_on_tiles(const tl_ctx *c) {
+  if (!(c->pair_tiled && c->nranks > 1 && c->comm_fused && c->g.hd >= 2)) return false;
   for (int r = 0; r < c->nranks; r++)
     if (c->rank_blob[r].nx < 2 || c->rank_blob[r].ny < 2) return false;
   return true;
 }
-template <int S, int MINB>
-static int launch_cheby_pair_tiled_ring(tl_ctx *c, const ChebyPairTiledParams &P) {
+// Two Chebyshev iterations = one kernel (option cheby_pair; k_cheby_pair_ring).  On tiles (TILED) the kernel
+// pushes u' two cells and p' one cell deep into the eight surrounding tiles and its tail is the rendezvous.
+static bool cheby_pairs_tiled(const tl_ctx *c) { return c->cheby_pair && pairs_on_tiles(c); }
+template <int S, int MINB, bool TILED>
+static int launch_cheby_pair_ring(tl_ctx *c, const ChebyPairParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
   static unsigned long long prepared = 0;
-  TRY(tl_prepare_smem(c, k_cheby_pair_tiled_ring<S, MINB>, smem, &prepared));
-  CU(c, tl_launch(c, k_cheby_pair_tiled_ring<S, MINB>, c->pair_grid, TL_FUSED_THREADS, smem, P));
+  TRY(tl_prepare_smem(c, k_cheby_pair_ring<S, MINB, TILED>, smem, &prepared));
+  CU(c, tl_launch(c, k_cheby_pair_ring<S, MINB, TILED>, c->pair_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }
-static int enqueue_cheby_pair_tiled(tl_ctx *c) {
-  ChebyPairTiledParams P;
+static int enqueue_cheby_pair(tl_ctx *c) {
+  ChebyPairParams P;
   P.c = cheby_params(c);
   P.c.t = c->pair_tiling;
-  P.push_ua = push8_for(c, TL_U); P.push_ub = push8_for(c, B_U1);
-  P.push_p0 = push8_for(c, TL_P); P.push_p1 = push8_for(c, B_P1);
-  TRY((launch_cheby_pair_tiled_ring<4, 2>(c, P)));
+  if (c->nranks > 1) {
+    P.push_ua = push8_for(c, TL_U); P.push_ub = push8_for(c, B_U1);
+    P.push_p0 = push8_for(c, TL_P); P.push_p1 = push8_for(c, B_P1);
+    TRY((launch_cheby_pair_ring<4, 2, true>(c, P)));
+  } else {
+    memset(&P.push_ua, 0, 4 * sizeof(Push8));
+    TRY((launch_cheby_pair_ring<4, 2, false>(c, P)));
+  }
   CHECK_LAUNCH(c);
   c->launches++;
   return TL_OK;
 }
-// halos the first pair reads: kx, ky, u0, p and the current u two cells deep, corner blocks included, plus
-// the neighbours' physical-top halo row in the tile-internal halo columns (ky(.., ny))
-static int cheby_pair_tiled_fill_halos(tl_ctx *c, int u_buf) {
-  const int bufs[5] = {TL_KX, TL_KY, TL_U0, TL_P, u_buf};
+// Halos the first pair kernel of a phase reads on tile-internal sides: the given buffers two cells deep, corner
+// blocks included, plus the neighbours' PHYSICAL-top halo row in the tile-internal halo columns (ky(.., ny) is read
+// by the redundant cells next to a physical top; tests/emulation/emulate_pair_tiled.py).  Ends with a rendezvous.
+static int pair_tiled_fill_halos(tl_ctx *c, const int *bufs, int nbufs) {
   TRY(tile_barrier(c));
-  TRY(pull_halo_wide(c, bufs, 5, 2));
-  for (int q = 0; q < 5; q++) {
+  TRY(pull_halo_wide(c, bufs, nbufs, 2));
+  for (int q = 0; q < nbufs; q++) {
     k_pull_halo_cols_top<<<1, 32, 0, c->stream>>>(c->g, 2, c->buf[bufs[q]], peer_face(c, 0, bufs[q]), peer_face(c, 1, bufs[q]));
     c->launches++;
     CHECK_LAUNCH(c);
@@ -1496,6 +1537,10 @@ static StopCfg switch_cfg(int max_iters, double eps, int presteps, double epslim
 
 extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double eps, int max_iters, int presteps,
                               double epslim, int errorswitch, tl_solve_info *info) {
+  if (TL_IS_MULTI(c))
+    return multi_solve(c, info, [&](tl_ctx *t, tl_solve_info *o, int) {
+      return tl_cheby_solve(t, coef, rx, ry, eps, max_iters, presteps, epslim, errorswitch, o);
+    });
   if (!c || !info) return TL_ERR_ARG;
   memset(info, 0, sizeof *info);
   CU(c, cudaSetDevice(c->device));
@@ -1561,9 +1606,11 @@ extern "C" int tl_cheby_solve(tl_ctx *c, int coef, double rx, double ry, double 
     if (tt_next & 1) TRY(enqueue_cheby_iteration(c));
     if (tiled_pairs) {
       const int step_now = 2 + (tt_next & 1);                       // cheby_step after the alignment step
-      TRY(cheby_pair_tiled_fill_halos(c, (step_now & 1) ? B_U1 : TL_U));   // the buffer the first pair reads (no pair ran yet)
+      // kx, ky, u0, p and the buffer the first pair reads u from (no pair ran yet)
+      const int bufs[5] = {TL_KX, TL_KY, TL_U0, TL_P, (step_now & 1) ? B_U1 : TL_U};
+      TRY(pair_tiled_fill_halos(c, bufs, 5));
     }
-    auto enq2 = [&]() { return tiled_pairs ? enqueue_cheby_pair_tiled(c) : enqueue_cheby_pair(c); };
+    auto enq2 = [&]() { return enqueue_cheby_pair(c); };
     auto stop2 = [&](const SolveState &s) { return !cheby_pair_allowed(s); };
     TRY(run_chunks(c, &c->g_cheby2, &c->g_cheby2_iters, std::max(1, c->graph_iters / 2), 1, enq2, stop2, &fin));
     done = tl_cheby_should_stop(fin);
@@ -1656,42 +1703,78 @@ static PpcgInnerParams ppcg_inner_params(tl_ctx *c) {
 // reads through the stencil (p'; sd0; sd'; r after the last inner step) and ends with the tile
 // exchange.  Legacy mode: depth-1 halo pulls -- r, p before the matvec (ordered by the preceding rr
 // allreduce) and sd before every inner step (ordered by a 1-double NCCL rendezvous).
-// does this context run the inner steps two per pass?
-static bool ppcg_pairs_enabled(const tl_ctx *c, int inner_steps) {
-  return c->ppcg_pair && c->nranks == 1 && inner_steps >= 2 && (inner_steps % 2) == 0;
+// does this context run the inner steps two per pass?  Single tile: always (option ppcg_pair); tiles: when the
+// pair kernels can run on them and the caller did not ask for a specific exchange depth (requested_depth = 0).
+static bool ppcg_pairs_enabled(const tl_ctx *c, int inner_steps, int requested_depth) {
+  if (!c->ppcg_pair || inner_steps < 2) return false;
+  if (c->nranks == 1) return true;
+  const int req = requested_depth > 0 ? requested_depth : c->ppcg_depth_k;
+  return req == 0 && pairs_on_tiles(c);
 }
-template <int S, int MINB>
+template <int S, int MINB, bool TILED>
 static int launch_ppcg_pair_ring(tl_ctx *c, const PpcgPairParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
   static unsigned long long prepared = 0;
-  TRY(tl_prepare_smem(c, k_ppcg_pair_ring<S, MINB>, smem, &prepared));
-  CU(c, tl_launch(c, k_ppcg_pair_ring<S, MINB>, c->pair_grid, TL_FUSED_THREADS, smem, P));
+  TRY(tl_prepare_smem(c, k_ppcg_pair_ring<S, MINB, TILED>, smem, &prepared));
+  CU(c, tl_launch(c, k_ppcg_pair_ring<S, MINB, TILED>, c->pair_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }
 // pair k of the npairs pairs of an outer iteration: sd alternates TL_SD / B_SD1 from TL_SD (where
 // k_ppcg_ur_sd writes it); r alternates TL_R / B_R1 phased so that the LAST pair writes TL_R
+static int ppcg_pair_rin(int k, int npairs) { return ((npairs - k) & 1) ? B_R1 : TL_R; }
 static PpcgPairParams ppcg_pair_params(tl_ctx *c, int k, int npairs) {
   PpcgPairParams P;
+  const int sout = (k & 1) ? TL_SD : B_SD1, rout = ppcg_pair_rin(k + 1, npairs);
   P.g = c->g; P.t = c->pair_tiling; P.st = c->st; P.alphas = c->ch_alphas; P.betas = c->ch_betas;
   P.sin = c->buf[(k & 1) ? B_SD1 : TL_SD];
-  P.sout = c->buf[(k & 1) ? TL_SD : B_SD1];
-  P.rin = c->buf[((npairs - k) & 1) ? B_R1 : TL_R];
-  P.rout = c->buf[((npairs - 1 - k) & 1) ? B_R1 : TL_R];
+  P.sout = c->buf[sout];
+  P.rin = c->buf[ppcg_pair_rin(k, npairs)];
+  P.rout = c->buf[rout];
   P.u = c->buf[TL_U]; P.kx = c->buf[TL_KX]; P.ky = c->buf[TL_KY]; P.partials = c->partials;
+  P.cd = comm_dev(c);
+  P.push_s = push8_for(c, sout); P.push_r = push8_for(c, rout);
   return P;
 }
+static int launch_ppcg_pair(tl_ctx *c, int k, int npairs) {
+  const PpcgPairParams P = ppcg_pair_params(c, k, npairs);
+  if (c->nranks > 1) return launch_ppcg_pair_ring<4, 2, true>(c, P);
+  return launch_ppcg_pair_ring<4, 2, false>(c, P);
+}
+// the single step that ends an odd number of inner steps: sd sits in the buffer npairs pairs left it in, r in TL_R
+static PpcgInnerParams ppcg_trailing_params(tl_ctx *c, int npairs) {
+  PpcgInnerParams P = ppcg_inner_params(c);
+  const int cur = (npairs & 1) ? B_SD1 : TL_SD, oth = (npairs & 1) ? TL_SD : B_SD1;
+  P.sda = c->buf[cur]; P.sdb = c->buf[oth];            // pp = inner_steps - 1 is even: reads sda, writes sdb
+  P.push_sda = push_for(c, cur); P.push_sdb = push_for(c, oth);
+  return P;
+}
+static int launch_ppcg_trailing(tl_ctx *c, int npairs) {
+  const PpcgInnerParams P = ppcg_trailing_params(c, npairs);
+  switch (c->ring_eff) {
+    case 3: TRY((launch_ppcg_inner_ring<3, 3>(c, P))); break;
+    case 4: TRY((launch_ppcg_inner_ring<4, 2>(c, P))); break;
+    case 6: TRY((launch_ppcg_inner_ring<6, 1>(c, P))); break;
+    default: return tl_fail(c, TL_ERR_STATE, "internal: ring depth %d", c->ring_eff);
+  }
+  return TL_OK;
+}
 
-static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k) {
+static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k, bool pairs) {
   const bool legacy = legacy_comm(c);
-  if (ppcg_pairs_enabled(c, inner_steps)) {
+  if (pairs) {
     const int npairs = inner_steps / 2;
     TRY(launch_cg_a<false>(c));
     PpcgUrParams U = ppcg_ur_params(c);
-    if (npairs & 1) { U.deep = 1; U.r_out = c->buf[B_R1]; U.d_sd = 1; U.d_r = 0; }   // r goes where the first pair reads it
+    const int rin0 = ppcg_pair_rin(0, npairs);       // r goes where the first pair reads it
+    if (c->nranks > 1) {                             // tiles: sd two cells / r one cell deep into the eight surrounding tiles
+      U.deep = 1; U.r_out = c->buf[rin0]; U.d_sd = 2; U.d_r = 1;
+      U.push_sd8 = push8_for(c, TL_SD); U.push_r8 = push8_for(c, rin0);
+    } else if (rin0 != TL_R) { U.deep = 1; U.r_out = c->buf[rin0]; U.d_sd = 1; U.d_r = 0; }
     CU(c, tl_launch(c, k_ppcg_ur_sd, c->pw_grid, TL_FUSED_THREADS, 0, U));
-    for (int k = 0; k < npairs; k++) TRY((launch_ppcg_pair_ring<4, 2>(c, ppcg_pair_params(c, k, npairs))));
+    for (int k = 0; k < npairs; k++) TRY(launch_ppcg_pair(c, k, npairs));
+    if (inner_steps & 1) TRY(launch_ppcg_trailing(c, npairs));
     CHECK_LAUNCH(c);
-    c->launches += 2 + npairs;
+    c->launches += 2 + npairs + (inner_steps & 1);
     return TL_OK;
   }
   if (depth_k > 1) {
@@ -1737,6 +1820,10 @@ static int ppcg_effective_depth(tl_ctx *c, int requested, int inner_steps) {
 
 extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double eps, int max_iters, int presteps,
                              double epslim, int errorswitch, int inner_steps, int halo_depth_k, tl_solve_info *info) {
+  if (TL_IS_MULTI(c))
+    return multi_solve(c, info, [&](tl_ctx *t, tl_solve_info *o, int) {
+      return tl_ppcg_solve(t, coef, rx, ry, eps, max_iters, presteps, epslim, errorswitch, inner_steps, halo_depth_k, o);
+    });
   if (!c || !info || inner_steps < 1 || halo_depth_k < 0) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_solve: bad argument");
   if (halo_depth_k > c->g.hd) return tl_fail(c, TL_ERR_ARG, "tl_ppcg_solve: halo_depth_k %d exceeds halo_depth %d", halo_depth_k, c->g.hd);
   if ((size_t)inner_steps + 2 > c->hist_len)   // the coefficient arrays were sized from max_iters at tl_create
@@ -1745,7 +1832,11 @@ extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double e
   memset(info, 0, sizeof *info);
   CU(c, cudaSetDevice(c->device));
   if (c->nranks > 1 && !c->comm_ready) return tl_fail(c, TL_ERR_STATE, "tile context used before tl_comm_connect");
-  const int depth_k = ppcg_effective_depth(c, halo_depth_k, inner_steps);
+  // Inner-step schedule: two steps per pass (pairs; on tiles that is an exchange every 2 steps) unless switched off or
+  // a specific exchange depth was requested; otherwise one kernel per step, grouped by the exchange depth on tiles.
+  const bool pairs = ppcg_pairs_enabled(c, inner_steps, halo_depth_k);
+  const int depth_k = pairs ? (c->nranks > 1 ? 2 : 1) : ppcg_effective_depth(c, halo_depth_k, inner_steps);
+  const bool dk_mode = !pairs && depth_k > 1;
   info->halo_depth_k = depth_k;
   max_iters = std::min(max_iters, c->max_iters);
   const long long l0 = c->launches;
@@ -1783,7 +1874,11 @@ extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double e
   k_state_begin<<<1, 1, 0, c->stream>>>(c->st, cfg, cgit, theta, inner_steps);
   c->launches++;
   CHECK_LAUNCH(c);
-  if (depth_k > 1) {
+  if (pairs && c->nranks > 1) {   // the pair kernels recompute cells in the tile-internal halos: kx, ky two deep there
+    const int kbufs[2] = {TL_KX, TL_KY};
+    TRY(pair_tiled_fill_halos(c, kbufs, 2));
+  }
+  if (dk_mode) {
     // the groups compute in the tile-internal halos: kx, ky are needed there, depth_k cells deep,
     // corner blocks included (CG.init! leaves them only partly defined, CG.jl:61-68)
     const int kbufs[2] = {TL_KX, TL_KY};
@@ -1794,18 +1889,18 @@ extern "C" int tl_ppcg_solve(tl_ctx *c, int coef, double rx, double ry, double e
       if (c->g_ppcg) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
     }
   }
-  auto enq = [&]() { return enqueue_ppcg_outer(c, inner_steps, depth_k); };
+  auto enq = [&]() { return enqueue_ppcg_outer(c, inner_steps, dk_mode ? depth_k : 1, pairs); };
   auto stop = [&](const SolveState &s) { return tl_should_stop(s.iter, s.red_rr, s.cfg); };
   const int chunk = std::max(1, c->graph_iters / 4);
-  if (c->g_ppcg && (c->g_ppcg_inner != inner_steps || c->g_ppcg_k != depth_k)) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
+  if (c->g_ppcg && (c->g_ppcg_inner != inner_steps || c->g_ppcg_k != (dk_mode ? depth_k : 1))) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
   c->g_ppcg_inner = inner_steps;
-  c->g_ppcg_k = depth_k;
-  const bool pairs = ppcg_pairs_enabled(c, inner_steps);
+  c->g_ppcg_k = dk_mode ? depth_k : 1;
   if (c->g_ppcg && c->g_ppcg_pairs != (int)pairs) { cudaGraphExecDestroy(c->g_ppcg); c->g_ppcg = nullptr; }
   c->g_ppcg_pairs = pairs;
-  TRY(run_chunks(c, &c->g_ppcg, &c->g_ppcg_iters, chunk, pairs ? 2 + inner_steps / 2 : 2 + inner_steps, enq, stop, &fin));
+  TRY(run_chunks(c, &c->g_ppcg, &c->g_ppcg_iters, chunk, pairs ? 2 + inner_steps / 2 + (inner_steps & 1) : 2 + inner_steps, enq, stop, &fin));
   TRY(cg_flush(c, fin.iter, false));
-  c->sd_cur = (pairs ? inner_steps / 2 : depth_k > 1 ? (inner_steps + depth_k - 1) / depth_k : inner_steps) & 1;
+  // which buffer holds sd now: every pair / trailing step / group / step flips it
+  c->sd_cur = (pairs ? inner_steps / 2 + (inner_steps & 1) : dk_mode ? (inner_steps + depth_k - 1) / depth_k : inner_steps) & 1;
   if (c->sd_cur) {
     LAUNCH_BASIC(c, k_copy, c->g, 1, c->buf[B_SD1], c->buf[TL_SD]);
     c->sd_cur = 0;
@@ -1830,6 +1925,7 @@ static int jacobi_init_async(tl_ctx *c, int coef, double rx, double ry) {
 }
 
 extern "C" int tl_jacobi_init(tl_ctx *c, int coef, double rx, double ry) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_jacobi_init(t, coef, rx, ry); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   TRY(jacobi_init_async(c, coef, rx, ry));
@@ -1838,6 +1934,7 @@ extern "C" int tl_jacobi_init(tl_ctx *c, int coef, double rx, double ry) {
 }
 
 extern "C" int tl_jacobi_iterate(tl_ctx *c, double *error) {
+  if (TL_IS_MULTI(c)) return multi_scalar(c, error, [&](tl_ctx *t, double *o) { return tl_jacobi_iterate(t, o); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   LAUNCH_BASIC(c, k_copy, c->g, 1, field_ptr(c, TL_U), c->buf[TL_R]);          // Jacobi.jl:64  r .= u
@@ -1888,6 +1985,8 @@ static int launch_jacobi_resid(tl_ctx *c, int force) {
 // Jacobi.driver! (the module's solve!), src/solvers/Jacobi.jl:7-31.
 // A graph holds 50 iteration kernels followed by the residual kernel of Jacobi.jl:16-21.
 extern "C" int tl_jacobi_solve(tl_ctx *c, int coef, double rx, double ry, double eps, int max_iters, tl_solve_info *info) {
+  if (TL_IS_MULTI(c))
+    return multi_solve(c, info, [&](tl_ctx *t, tl_solve_info *o, int) { return tl_jacobi_solve(t, coef, rx, ry, eps, max_iters, o); });
   if (!c || !info) return TL_ERR_ARG;
   memset(info, 0, sizeof *info);
   CU(c, cudaSetDevice(c->device));
@@ -1939,6 +2038,7 @@ __global__ void k_state_for_timing(SolveState *st, double *hist_rr, double *hist
 }
 
 extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *avg_ms) {
+  if (TL_IS_MULTI(c)) return multi_max(c, avg_ms, [&](tl_ctx *t, double *o) { return tl_time_kernel(t, kernel, reps, o); });
   if (!c || !kernel || reps < 1 || !avg_ms) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   const std::string k(kernel);
@@ -1951,7 +2051,7 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
     else if (k == "cg_fused_r") TRY(launch_cg_b(c));
     else if (k == "cheby_fused") TRY(launch_cheby<false>(c));
     else if (k == "cheby_pair") { TRY(enqueue_cheby_pair(c)); c->launches--; }
-    else if (k == "ppcg_pair") TRY((launch_ppcg_pair_ring<4, 2>(c, ppcg_pair_params(c, 0, 2))));
+    else if (k == "ppcg_pair") TRY(launch_ppcg_pair(c, 0, 2));
     else if (k == "ppcg_inner") TRY(launch_ppcg_inner(c));
     else if (k == "jacobi_fused") { TRY(launch_jacobi(c)); c->launches--; }
     else return tl_fail(c, TL_ERR_ARG, "tl_time_kernel: unknown kernel %s", kernel);
@@ -1978,6 +2078,7 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
 }
 
 extern "C" int tl_timer_start(tl_ctx *c) {
+  if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_timer_start(t); });
   if (!c) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -1986,6 +2087,7 @@ extern "C" int tl_timer_start(tl_ctx *c) {
 }
 
 extern "C" int tl_timer_stop(tl_ctx *c, double *elapsed_ms) {
+  if (TL_IS_MULTI(c)) return multi_max(c, elapsed_ms, [&](tl_ctx *t, double *o) { return tl_timer_stop(t, o); });
   if (!c || !elapsed_ms) return TL_ERR_ARG;
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaEventRecord(c->ev_t1, c->stream));
@@ -1997,7 +2099,10 @@ extern "C" int tl_timer_stop(tl_ctx *c, double *elapsed_ms) {
 }
 
 extern "C" int tl_launch_count(tl_ctx *c, long long *count) {
+  if (TL_IS_MULTI(c) && count) return multi_launch_count(c, count);
   if (!c || !count) return TL_ERR_ARG;
   *count = c->launches;
   return TL_OK;
 }
+
+#include "tl_multi.inl"

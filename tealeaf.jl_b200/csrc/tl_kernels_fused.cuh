@@ -375,7 +375,8 @@ struct PpcgInnerParams {
   Push push_sda, push_sdb, push_r;
 };
 
-// TWO inner steps in one pass (k_ppcg_pair_ring, tl_kernels_ring.cuh; single tile, even inner_steps):
+// TWO inner steps in one pass (k_ppcg_pair_ring, tl_kernels_ring.cuh; an odd inner_steps ends with one
+// k_ppcg_inner_ring step):
 //   step A (pp):    rA = r - A sd ;   uA = u + sd ;   sA = alpha_pp sd + beta_pp rA
 //   step B (pp+1):  rB = rA - A sA ;  uB = uA + sA ;  sB = alpha_pp+1 sA + beta_pp+1 rB
 // ~32 B per cell-step instead of 64.  sA is recomputed redundantly at warp-task borders (needs the
@@ -388,6 +389,8 @@ struct PpcgPairParams {
   const double *sin; double *sout; const double *rin; double *rout;
   double *u; const double *kx; const double *ky;
   double *partials;
+  const CommDev *cd;           // tiles (TILED instantiation): exchange in the tail
+  Push8 push_s, push_r;        // halo targets of sout / rout on the eight surrounding tiles
 };
 
 // Matrix-powers variant of the inner steps for tiles (k_ppcg_inner_dk): the steps are grouped by

@@ -475,141 +475,23 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
 // Because neighbouring warps still need the OLD p, p is written out of place (p <-> p1) as u is.
 // Step A is never a norm iteration (norm iterations have odd tt, Cheby.jl:40-51, and the host
 // starts pairs on even tt); step B may be: its norm is summed from registers, and w / r are
-// stored when its state is observable, exactly as in k_cheby_fused_ring.  Single tile only.
+// stored when its state is observable, exactly as in k_cheby_fused_ring.
+//
+// TILED = true is the same pass on a TILE of a decomposed mesh (multi-GPU): on tile-internal sides
+// nothing is clamped -- the window columns -2, -1 / nx, nx+1 and the rows -2, -1 / ny, ny+1 are read
+// from the halo, which holds the neighbours' u two cells deep (corner blocks included), p and u0 one
+// cell deep and kx, ky two deep (tests/emulation/emulate_pair_tiled.py proves these depths sufficient
+// and necessary).  u' and p' are pushed that deep into the EIGHT surrounding tiles from step B, and
+// the mailbox exchange in the tail is the completion barrier -- ONE rendezvous per two iterations:
+// the pair kernel is the depth-2 matrix-powers Chebyshev step.
 // ------------------------------------------------------------------------------------------
 #define TL_PAIR_OWN 60   // owned columns per warp (window: 64)
-template <int S, int MINB>
-__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_ring(const ChebyParams P) {
-  tl_pdl_entry();
-  extern __shared__ __align__(128) unsigned char ring_raw[];
-  __shared__ double sm[32];
-  SolveState *st = P.st;
-  const int step = st->cheby_step;
-  if (st->comm_error || tl_cheby_should_stop(*st)) return;
-  const int ttA = st->cheby_tt0 + step - 1;
-  if (ttA + 1 > st->cheby_max_tt) return;                                            // step B not permitted
-  if (tl_cheby_is_norm_iter(step, st->cheby_tt0, st->cheby_est)) return;            // never (see above): guard
-  const double alphaA = P.alphas[step], betaA = P.betas[step];
-  const double alphaB = P.alphas[step + 1], betaB = P.betas[step + 1];
-  const bool calc_norm = tl_cheby_is_norm_iter(step + 1, st->cheby_tt0, st->cheby_est);
-  const bool store_wr = calc_norm || (ttA + 1 == st->cheby_max_tt);
-  const int pairs = st->cheby_pairs;
-  const int upar = tl_cheby_u_parity(step, pairs);
-  const double *__restrict__ uin = upar ? P.ub : P.ua;
-  double *__restrict__ uout = upar ? P.ua : P.ub;
-  const double *__restrict__ pin = (pairs & 1) ? P.p1 : P.p;
-  double *__restrict__ pout = (pairs & 1) ? P.p : P.p1;
-  const double *__restrict__ u0 = P.u0;
-  const double *__restrict__ kx = P.kx;
-  const double *__restrict__ ky = P.ky;
-  const Geo g = P.g;
-  const int pitch = g.pitch;
-  const bool physL = g.phys & TL_PHYS_LEFT, physR = g.phys & TL_PHYS_RIGHT;
-  const bool physB = g.phys & TL_PHYS_BOTTOM, physT = g.phys & TL_PHYS_TOP;
-
-  double acc[1] = {0.0};
-  const int lane = threadIdx.x & 31;
-  const int wt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (wt < P.t.nstrips * P.t.nchunks) {
-    const int s = wt % P.t.nstrips, q = wt / P.t.nstrips;
-    const int j0 = q * P.t.rows_per_chunk, j1 = min(g.ny, j0 + P.t.rows_per_chunk);
-    const int own_lo = s * TL_PAIR_OWN, own_hi = min(g.nx, own_lo + TL_PAIR_OWN);
-    MarchCtx m;                            // the WINDOW: what is loaded and computed
-    m.lane = lane;
-    m.i0 = own_lo - 2 + 2 * lane;
-    m.j0 = j0; m.j1 = j1;
-    m.ld_ok = m.i0 <= g.nx;                // the pair (nx, nx+1) is still inside the padded row
-    m.acta = m.ld_ok;                      // RingMarch loads the pointwise fields as pairs
-    m.actb = m.ld_ok;
-    m.ecol = 0; m.has_edge = false;        // no edge loads: neighbours come from the window
-    MarchCtx mo = m;                       // the OWNED cells: what is stored
-    mo.acta = m.i0 >= own_lo && m.i0 < own_hi;
-    mo.actb = m.i0 + 1 >= own_lo && m.i0 + 1 < own_hi && mo.acta;
-    if (j0 < j1) {
-      const double2 z2 = make_double2(0.0, 0.0);
-      // rows on which uA is needed: the chunk plus one row below / above (not beyond a physical side)
-      const int ja_lo = (j0 == 0 && physB) ? 0 : j0 - 1;
-      const int ja_hi = (j1 == g.ny && physT) ? g.ny - 1 : j1;
-      RingMarch<S> rg;
-      rg.init(ring_raw, m);
-      double2 Um, Uc, kyc;
-      {
-        const int jm = (ja_lo == 0 && physB) ? 0 : ja_lo - 1;
-        const long om = (long)jm * pitch + m.i0, oc = (long)ja_lo * pitch + m.i0;
-        Um = m.ld_ok ? tl_ld2(uin + om) : z2;
-        Uc = m.ld_ok ? tl_ld2(uin + oc) : z2;
-        kyc = m.ld_ok ? tl_ld2(ky + oc) : z2;
-      }
-#pragma unroll
-      for (int d = 0; d < S - 1; d++) {
-        if (ja_lo + d <= ja_hi) rg.issue(g, m, physT, ja_lo + d, d, uin, ky, kx, u0, pin);
-        tl_cp_commit();
-      }
-      // carried from the previous row (row j = jj - 1 of step B): uA(j-1), uA(j), pA(j), u0(j), kx(j), ky(j)
-      double2 Am = z2, Ac = z2, pAc = z2, u0c = z2, kxc = z2, kyB = z2;
-      auto step_b = [&](int j, double2 An, double2 kyn) {
-        const double2 Bm = (j == 0 && physB) ? Ac : Am;          // uA(-1) := uA(0)
-        double wa, wb;
-        tl_stencil2(g, m, physL, physR, Bm, Ac, An, 0.0, kxc, 0.0, kyB, kyn, wa, wb);
-        const double ra = u0c.x - wa, rb = u0c.y - wb;
-        const double2 pn = make_double2(alphaB * pAc.x + betaB * ra, alphaB * pAc.y + betaB * rb);
-        const double2 un = make_double2(Ac.x + pn.x, Ac.y + pn.y);
-        const long oc = (long)j * pitch + m.i0;
-        if (mo.actb) {
-          tl_st2(pout + oc, pn);
-          tl_st2(uout + oc, un);
-          if (store_wr) { tl_st2(P.w + oc, make_double2(wa, wb)); tl_st2(P.r + oc, make_double2(ra, rb)); }
-          acc[0] += ra * ra; acc[0] += rb * rb;
-        } else if (mo.acta) {
-          pout[oc] = pn.x; uout[oc] = un.x;
-          if (store_wr) { P.w[oc] = wa; P.r[oc] = ra; }
-          acc[0] += ra * ra;
-        }
-        tl_reflect_edges(uout, g, mo, j, oc, un);                // haloupdate!(.., [:u]) Cheby.jl:55/:78
-      };
-      for (int jj = ja_lo; jj <= ja_hi; jj++) {
-        if (jj + S - 1 <= ja_hi) rg.issue(g, m, physT, jj + S - 1, rg.fill, uin, ky, kx, u0, pin);
-        tl_cp_commit();
-        tl_cp_wait<S - 1>();
-        const RingRow cur = rg.take(m, true, true);              // x = u(jj+1), ky = ky(jj+1), kx = kx(jj), a = u0(jj), b = p(jj)
-        double wa, wb;
-        tl_stencil2(g, m, physL, physR, Um, Uc, cur.x, 0.0, cur.kx, 0.0, kyc, cur.ky, wa, wb);
-        const double ra = cur.a.x - wa, rb = cur.a.y - wb;
-        const double2 pA = make_double2(alphaA * cur.b.x + betaA * ra, alphaA * cur.b.y + betaA * rb);
-        const double2 uA = make_double2(Uc.x + pA.x, Uc.y + pA.y);
-        if (jj - 1 >= j0) step_b(jj - 1, uA, kyc);               // kyc = ky(jj) = ky(j+1)
-        Am = Ac; Ac = uA; pAc = pA; u0c = cur.a; kxc = cur.kx; kyB = kyc;
-        Um = Uc; Uc = cur.x; kyc = cur.ky;
-      }
-      // top row of a physical top: uA(ny) := uA(ny-1)
-      if (ja_hi == j1 - 1) step_b(j1 - 1, Ac, kyc);
-      tl_cp_wait<0>();
-    }
-  }
-  if (tl_kernel_tail(acc, calc_norm, st, P.partials, nullptr, sm)) {
-    if (calc_norm) {
-      st->red_norm_local = acc[0];
-      st->red_norm = acc[0];
-    }
-    st->cheby_step = step + 2;
-    st->cheby_pairs = pairs + 1;
-  }
-}
-
-// The same two-iteration pass on a TILE of a decomposed mesh (EXPERIMENTAL: option pair_tiled, off; written from
-// the multi-tile emulation tests/emulation/emulate_pair_tiled.py, not yet run on a GPU).  On tile-internal
-// sides nothing is clamped: the window columns -2, -1 / nx, nx+1 and the rows -2, -1 / ny, ny+1 are read from
-// the halo, which holds the neighbours' u two cells deep (corner blocks included), p and u0 one cell deep and
-// kx, ky two deep.  u' and p' are pushed that deep into the eight surrounding tiles from step B, and the
-// mailbox exchange in the tail is the completion barrier -- ONE rendezvous per two iterations: this is
-// the depth-2 matrix-powers Chebyshev step.  Kept as a separate kernel so that the verified single-tile
-// kernel above stays byte-identical.
-struct ChebyPairTiledParams {
+struct ChebyPairParams {
   ChebyParams c;
-  Push8 push_ua, push_ub, push_p0, push_p1;
+  Push8 push_ua, push_ub, push_p0, push_p1;   // TILED: halo targets of the u / p buffer being written
 };
-template <int S, int MINB>
-__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_tiled_ring(const ChebyPairTiledParams PT) {
+template <int S, int MINB, bool TILED>
+__global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_ring(const ChebyPairParams PT) {
   const ChebyParams &P = PT.c;
   tl_pdl_entry();
   extern __shared__ __align__(128) unsigned char ring_raw[];
@@ -651,7 +533,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_tiled_rin
     m.lane = lane;
     m.i0 = own_lo - 2 + 2 * lane;
     m.j0 = j0; m.j1 = j1;
-    m.ld_ok = m.i0 <= g.nx + (physR ? 0 : 1);   // tile-internal right side, odd nx: u(nx+1) sits in the pair (nx+1, nx+2)
+    // the pair (nx, nx+1) is still inside the padded row; on a tile-internal right side with odd nx, u(nx+1)
+    // sits in the pair (nx+1, nx+2)
+    m.ld_ok = m.i0 <= g.nx + ((TILED && !physR) ? 1 : 0);
     m.acta = m.ld_ok;                      // RingMarch loads the pointwise fields as pairs
     m.actb = m.ld_ok;
     m.ecol = 0; m.has_edge = false;        // no edge loads: neighbours come from the window
@@ -699,9 +583,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_tiled_rin
           acc[0] += ra * ra;
         }
         tl_reflect_edges(uout, g, mo, j, oc, un);                // haloupdate!(.., [:u]) Cheby.jl:55/:78
-        // tile-internal sides: the next pass reads u two cells deep (corner blocks included) and p one cell deep
-        tl_push_deep(push_u, g, 2, m.i0, mo.acta, mo.actb, j, un);
-        tl_push_deep(push_p, g, 1, m.i0, mo.acta, mo.actb, j, pn);
+        if (TILED) {   // tile-internal sides: the next pass reads u two cells deep (corner blocks included), p one cell deep
+          tl_push_deep(push_u, g, 2, m.i0, mo.acta, mo.actb, j, un);
+          tl_push_deep(push_p, g, 1, m.i0, mo.acta, mo.actb, j, pn);
+        }
       };
       for (int jj = ja_lo; jj <= ja_hi; jj++) {
         if (jj + S - 1 <= ja_hi) rg.issue(g, m, physT, jj + S - 1, rg.fill, uin, ky, kx, u0, pin);
@@ -722,7 +607,8 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_tiled_rin
       tl_cp_wait<0>();
     }
   }
-  if (tl_kernel_tail(acc, calc_norm, st, P.partials, P.cd, sm)) {   // tiles: all-tiles norm / completion barrier
+  // tiles: all-tiles norm / completion barrier of the halo pushes
+  if (tl_kernel_tail(acc, calc_norm, st, P.partials, TILED ? P.cd : nullptr, sm)) {
     if (calc_norm) {
       st->red_norm_local = acc[0];
       st->red_norm = acc[0];
@@ -733,8 +619,11 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_tiled_rin
 }
 
 // Two PPCG inner steps in one pass (algorithm: PpcgPairParams in tl_kernels_fused.cuh; window,
-// carry and clamp scheme: k_cheby_pair_ring above).
-template <int S, int MINB>
+// carry and clamp scheme: k_cheby_pair_ring above).  TILED: sd is read two cells deep (corner blocks
+// included) and r one cell deep from the tile-internal halos, kx / ky two deep; step B pushes sd' and r'
+// that deep into the eight surrounding tiles (after the last pair of an outer iteration only r, one cell
+// deep: the next matvec reads it), and the tail's exchange is the completion barrier.
+template <int S, int MINB, bool TILED>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_pair_ring(const PpcgPairParams P) {
   tl_pdl_entry();
   extern __shared__ __align__(128) unsigned char ring_raw[];
@@ -769,7 +658,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_pair_ring(const
     m.lane = lane;
     m.i0 = own_lo - 2 + 2 * lane;
     m.j0 = j0; m.j1 = j1;
-    m.ld_ok = m.i0 <= g.nx;
+    m.ld_ok = m.i0 <= g.nx + ((TILED && !physR) ? 1 : 0);   // as in k_cheby_pair_ring
     m.acta = m.ld_ok;
     m.actb = m.ld_ok;
     m.ecol = 0; m.has_edge = false;
@@ -815,6 +704,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_pair_ring(const
         }
         // halo(sd) of PPCG.jl:76 happens BEFORE each inner step (see k_ppcg_inner_ring)
         tl_reflect_edges(sout, g, mo, j, oc, last ? Ac : sn);
+        if (TILED) {
+          if (!last) tl_push_deep(P.push_s, g, 2, m.i0, mo.acta, mo.actb, j, sn);
+          tl_push_deep(P.push_r, g, 1, m.i0, mo.acta, mo.actb, j, rn);
+        }
       };
       for (int jj = ja_lo; jj <= ja_hi; jj++) {
         if (jj + S - 1 <= ja_hi) rg.issue(g, m, physT, jj + S - 1, rg.fill, sin, ky, kx, rin, u);
@@ -834,7 +727,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_pair_ring(const
       tl_cp_wait<0>();
     }
   }
-  if (tl_kernel_tail(acc, last, st, P.partials, nullptr, sm)) {
+  if (tl_kernel_tail(acc, last, st, P.partials, TILED ? P.cd : nullptr, sm)) {
     if (last) {
       st->red_rr_local = acc[0];      // PPCG.jl:88
       st->red_rr = acc[0];

@@ -38,6 +38,29 @@ class DeviceChunk:
         self.cgalpha = np.zeros(maxiters)  # chunk.cgα / cgβ, src/chunk.jl:56-57
         self.cgbeta = np.zeros(maxiters)
 
+    @classmethod
+    def multi(cls, xcells: int, ycells: int, halodepth: int = 2, maxiters: int = 10_000, ngpus: int = 2, devices=None,
+              px: int = 0, py: int = 0, **_):
+        """ONE chunk of the global mesh spread over `ngpus` GPUs of this process (`tl_create_multi`): same methods,
+        `set_field` / `get_field` scatter / gather the global arrays.  `devices` may repeat an index (tiles sharing
+        one GPU: test mode, needs CUDA_MODULE_LOADING=EAGER)."""
+        self = cls.__new__(cls)
+        self._l = _lib.load()
+        self.nx, self.ny, self.hd = xcells, ycells, halodepth
+        self.x, self.y = xcells + 2 * halodepth, ycells + 2 * halodepth
+        self.maxiters = maxiters
+        self.rank, self.px, self.py = 0, px, py
+        ctx = C.c_void_p()
+        dev = (C.c_int * ngpus)(*devices) if devices is not None else None
+        rc = self._l.tl_create_multi(C.byref(ctx), xcells, ycells, halodepth, maxiters, ngpus, dev, px, py)
+        if rc != _lib.TL_OK:
+            raw = self._l.tl_last_error(None)
+            raise _lib.TeaLeafError(rc, "tl_create_multi failed: " + (raw.decode() if raw else ""))
+        self.ctx = ctx
+        self.cgalpha = np.zeros(maxiters)
+        self.cgbeta = np.zeros(maxiters)
+        return self
+
     # ---- lifetime ----
     def close(self):
         if getattr(self, "ctx", None):

@@ -50,6 +50,7 @@ class PaintState(C.Structure):
 SIGNATURES = {
     "tl_create": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I]),
     "tl_create_tile": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _I, _I, _I]),
+    "tl_create_multi": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, C.POINTER(_I), _I, _I]),
     "tl_destroy": (None, [_P]),
     "tl_last_error": (C.c_char_p, [_P]),
     "tl_abi_version": (_I, []),

@@ -163,7 +163,11 @@ def _properties(chunk, hd=2):
     u0 = chunk.get_field("u0")
     r = chunk.get_field("r")
     ui, u0i, ri = u[hd:-hd, hd:-hd], u0[hd:-hd, hd:-hd], r[hd:-hd, hd:-hd]
-    assert abs((u0i.sum() - ui.sum()) - ri.sum()) <= 1e-11 * abs(u0i.sum())
+    k = np.unravel_index(np.abs(ri).argmax(), ri.shape)
+    diag = dict(sum_u0_minus_u=float(u0i.sum() - ui.sum()), sum_r=float(ri.sum()), rmax=float(np.abs(ri).max()), at=tuple(int(v) for v in k),
+                sum_r_edges=[float(ri[0, :].sum()), float(ri[-1, :].sum()), float(ri[:, 0].sum()), float(ri[:, -1].sum())],
+                sum_r_inner=float(ri[1:-1, 1:-1].sum()), n_big=int((np.abs(ri) > 1e-9).sum()))
+    assert abs((u0i.sum() - ui.sum()) - ri.sum()) <= 1e-11 * abs(u0i.sum()), diag
     assert ui.min() > 0
     np.testing.assert_array_equal(u[hd - 1, hd:-hd], u[hd, hd:-hd])      # reflected halos (haloupdate! u)
     np.testing.assert_array_equal(u[hd:-hd, -hd], u[hd:-hd, -hd - 1])

@@ -422,7 +422,9 @@ def test_cheby_pair_is_bit_identical(nx, ny, over):
 
 
 @pytest.mark.parametrize("nx,ny,inner,over", [(128, 128, 10, {}), (96, 160, 4, {}), (65, 70, 6, {}), (257, 19, 2, {}), (61, 300, 10, {}),
-                                              (700, 523, 10, {"maxiters": 700}), (1500, 1100, 8, {"maxiters": 900})])
+                                              (128, 128, 7, {}), (96, 160, 3, {}), (257, 19, 5, {}),      # odd: pairs + one trailing single step
+                                              (700, 523, 10, {"maxiters": 700}), (1500, 1100, 8, {"maxiters": 900}),
+                                              (1500, 1100, 9, {"maxiters": 900})])
 def test_ppcg_pair_is_bit_identical(nx, ny, inner, over):
     """Option ppcg_pair: two PPCG inner steps per pass (k_ppcg_pair_ring).  Per-cell arithmetic is identical
     to one kernel per inner step; the outer iteration's sum(r.r) is added up over different warp tasks and

@@ -85,3 +85,22 @@ def test_two_devices_in_one_process():
         assert o[0] == outs[0][0] and o[1] == outs[0][1]
         np.testing.assert_array_equal(o[2], outs[0][2])
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver,over", [("cg", {}), ("cheby", {}), ("ppcg", {"ppcginnersteps": 6})])
+def test_one_context_over_all_gpus_of_the_box(solver, over):
+    """tl_create_multi on real GPUs: ONE process, ONE context, one tile per GPU (peer access between the devices of the
+    process); host code identical to the single-GPU code."""
+    import torch
+    n = min(torch.cuda.device_count(), 8)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    from tealeaf_jl_b200.device import DeviceChunk
+    from oracle.oracle import OracleChunk
+    from test_gpu_parity import assert_parity, run
+    s = lambda: classic_settings(384, ny=320, steps=2, solver=solver, **over)
+    dev = run(lambda *a, **k: DeviceChunk.multi(*a, ngpus=n, **k), s())
+    ora = run(OracleChunk, s())
+    assert_parity(dev, ora, iter_slack=1 if solver == "cg" else 0)
+    dev[0].close()

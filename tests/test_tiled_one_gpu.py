@@ -7,8 +7,6 @@ PPCG groups -- so the decomposition logic is covered by the single-GPU `-m gpu` 
 
 Every case is checked against the single-chunk CPU oracle with the north-star bar: identical
 iteration counts (CG: +-1), per-step summaries within 1e-10, u / energy within 1e-9."""
-import os
-
 import numpy as np
 import pytest
 
@@ -134,32 +132,59 @@ def test_ppcg_depth_k_is_bit_identical_to_depth_1(grid, nx, ny, inner, hd, k):
 
 
 @pytest.mark.timeout(600)
-def test_ppcg_depth_k_two_timesteps_default_auto():
-    """halo_depth_k = 0 (automatic) picks halo_depth; state carried across timesteps."""
+def test_ppcg_default_schedule_two_timesteps():
+    """halo_depth_k = 0 (automatic): two inner steps per pass on the tiles (an exchange every 2 steps); with the pair
+    kernels switched off, matrix-powers groups of halo_depth steps.  State carried across timesteps."""
     over = {"ppcginnersteps": 6, "halodepth": 3}
+    ref = run_oracle("ppcg", 140, 120, steps=2, over=over)
     got = run_tiled((2, 2), "ppcg", 140, 120, steps=2, over=over)
+    assert [r["halo_depth_k"] for r in got[0]] == [2, 2]
+    check_against_oracle(got, ref, "ppcg", hd=3)
+    got = run_tiled((2, 2), "ppcg", 140, 120, steps=2, over=over, options={"ppcg_pair": 0})
     assert [r["halo_depth_k"] for r in got[0]] == [3, 3]
-    check_against_oracle(got, run_oracle("ppcg", 140, 120, steps=2, over=over), "ppcg", hd=3)
+    check_against_oracle(got, ref, "ppcg", hd=3)
 
 
-# ---- EXPERIMENTAL: two Chebyshev iterations per pass on tiles (option pair_tiled) ------------------------
-# Written from the multi-tile emulation (tests/emulation/emulate_pair_tiled.py) after the round's GPU budget was
-# spent: not yet run on a GPU, off by default, and therefore not part of the default suite.  First thing to
-# run in the next round:  TL_EXPERIMENTAL=1 python -m pytest tests/test_tiled_one_gpu.py -m gpu -k tiled_cheby_pairs
+# ---- temporal blocking on tiles: two Chebyshev iterations / PPCG inner steps per pass, depth-2 exchange ----------
 PAIR_TILED_CASES = [((1, 2), 192, 256, 2), ((2, 1), 130, 77, 2), ((2, 2), 129, 67, 2), ((2, 2), 200, 150, 3), ((3, 3), 200, 190, 2),
                     ((1, 4), 96, 256, 2), ((4, 1), 301, 64, 2)]
 
 
-@pytest.mark.skipif(os.environ.get("TL_EXPERIMENTAL") != "1", reason="pair_tiled has not been run on a GPU yet (TL_EXPERIMENTAL=1)")
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("grid,nx,ny,hd", PAIR_TILED_CASES, ids=[f"{g[0]}x{g[1]}-{nx}x{ny}-hd{hd}" for g, nx, ny, hd in PAIR_TILED_CASES])
 def test_tiled_cheby_pairs_are_bit_identical(grid, nx, ny, hd):
+    """k_cheby_pair_ring<.., TILED>: every field bit-identical to one kernel (and one exchange) per iteration."""
     over = {"halodepth": hd}
     fields = ("u", "energy", "p", "w", "r")
     base = run_tiled(grid, "cheby", nx, ny, over=over, options={"pair_tiled": 0}, fields=fields)
-    pair = run_tiled(grid, "cheby", nx, ny, over=over, options={"pair_tiled": 1}, fields=fields)
+    pair = run_tiled(grid, "cheby", nx, ny, over=over, fields=fields)      # default: pairs on tiles
     assert [(r["iters"], r["cg_iters"], r["cheby_iters"]) for r in base[0]] == [(r["iters"], r["cg_iters"], r["cheby_iters"]) for r in pair[0]]
     assert sum(r["kernel_launches"] for r in pair[0]) < sum(r["kernel_launches"] for r in base[0])
     for f in fields:
         np.testing.assert_array_equal(base[2][f][hd:-hd, hd:-hd], pair[2][f][hd:-hd, hd:-hd], err_msg=f)
     check_against_oracle(pair, run_oracle("cheby", nx, ny, over=over), "cheby", hd=hd)
+
+
+PPCG_PAIR_TILED_CASES = [((1, 2), 192, 160, 2, 6), ((2, 1), 130, 77, 2, 5), ((2, 2), 129, 67, 2, 10), ((2, 2), 200, 150, 3, 7),
+                         ((3, 3), 200, 190, 2, 4), ((1, 4), 96, 256, 2, 3), ((4, 1), 301, 64, 4, 2)]
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("grid,nx,ny,hd,inner", PPCG_PAIR_TILED_CASES,
+                         ids=[f"{g[0]}x{g[1]}-{nx}x{ny}-hd{hd}-inner{n}" for g, nx, ny, hd, n in PPCG_PAIR_TILED_CASES])
+def test_tiled_ppcg_pairs_match(grid, nx, ny, hd, inner):
+    """k_ppcg_pair_ring<.., TILED> (+ the trailing single step of an odd count): same iteration counts as one kernel and
+    one exchange per inner step; fields agree to the rounding of the outer dot products (summed over different warp
+    tasks), and both match the oracle."""
+    over = {"halodepth": hd, "ppcginnersteps": inner}
+    fields = ("u", "energy", "p", "sd", "r")
+    base = run_tiled(grid, "ppcg", nx, ny, over={**over, "ppcghalodepth": 1}, fields=fields)
+    pair = run_tiled(grid, "ppcg", nx, ny, over=over, fields=fields)
+    assert [r["halo_depth_k"] for r in base[0]] == [1] and [r["halo_depth_k"] for r in pair[0]] == [2]
+    key = lambda recs: [(r["iters"], r["cg_iters"], r["cheby_iters"], r["inner_total"]) for r in recs]
+    assert key(base[0]) == key(pair[0])
+    assert sum(r["kernel_launches"] for r in pair[0]) < sum(r["kernel_launches"] for r in base[0])
+    scale = np.abs(base[2]["u"]).max()
+    for f in fields:
+        assert np.abs(base[2][f][hd:-hd, hd:-hd] - pair[2][f][hd:-hd, hd:-hd]).max() <= 1e-11 * scale, f
+    check_against_oracle(pair, run_oracle("ppcg", nx, ny, over=over), "ppcg", hd=hd)
