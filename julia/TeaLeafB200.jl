@@ -262,6 +262,71 @@ function TeaLeaf.setchunkstate!(chunk::B200Chunk, set::Settings; x0::Int = 0, y0
                        chunk.ctx, length(cs), cs, set.xmin, set.ymin, set.dx, set.dy, x0, y0))
 end
 
+# ---- debugrecord (src/TeaLeaf.jl:90-107) for the device chunk ----------------------------------------------
+"""
+    debugrecord(settings, chunk::B200Chunk)
+
+The reference's `--debug-out` dump: every `Chunk` attribute in declaration order (src/chunk.jl:19-60), matrices one
+column per line.  The 11 device fields come through `download`; `density0` and `mi` (never written on the path) are
+zeros, geometry vectors are rebuilt as `Chunk(settings)` builds them (src/chunk.jl:76-77), `xarea` / `yarea` are
+skipped (never filled consistently, never read).
+"""
+function TeaLeaf.debugrecord(settings::Settings, chunk::B200Chunk)
+    settings.debugfile == "" && return
+    @info "Writing debug data to $(settings.debugfile)"
+    z = zeros(chunk.x, chunk.y)
+    mat(a) = join(join.(eachcol(a), ' '), '\n')              # getstring, src/TeaLeaf.jl:104-106
+    vx = @. settings.xmin + settings.dx * ((1:chunk.x+1) - settings.halodepth - 1)
+    vy = @. settings.ymin + settings.dy * ((1:chunk.y+1) - settings.halodepth - 1)
+    open(settings.debugfile, write = true, append = true) do f
+        item(name, text) = (println(f, name); println(f, text); println(f, ""))
+        item("density0", mat(z))
+        for fld in (:density, :energy0, :energy, :u, :u0, :p, :r)
+            item(String(fld), mat(download(chunk, fld)))
+        end
+        item("mi", mat(z))
+        for fld in (:w, :kx, :ky, :sd)
+            item(String(fld), mat(download(chunk, fld)))
+        end
+        item("vertexx", join(vx, ' ')); item("vertexy", join(vy, ' '))
+        item("cellx", join(0.5 .* (vx[1:end-1] .+ vx[2:end]), ' '))
+        item("celly", join(0.5 .* (vy[1:end-1] .+ vy[2:end]), ' '))
+        item("volume", mat(fill(chunk.volume, chunk.x, chunk.y)))
+        item("θ", string(0.0)); item("eigmin", string(chunk.eigmin)); item("eigmax", string(chunk.eigmax))
+        item("cgα", join(chunk.cgα, ' ')); item("cgβ", join(chunk.cgβ, ' '))
+        item("chebyα", join(zeros(length(chunk.cgα)), ' ')); item("chebyβ", join(zeros(length(chunk.cgα)), ' '))
+        print(f, "\n\n")
+    end
+end
+
+# ---- diffuse! (src/TeaLeaf.jl:62-83) for the device chunk -------------------------------------------------
+"""
+    diffuse!(chunk::B200Chunk, settings)
+
+The reference's timestep loop, line for line, as a method for the device chunk (so `diffuse!`'s `::Chunk` signature
+needs no edit), plus the one thing the reference parses and never uses: `end_time` (src/settings.jl:58).  As upstream
+TeaLeaf does, the loop also ends once the simulated time `tt * dtinit` reaches `settings.endtime`; the timestep is
+constant (`initial_timestep`; the reference has no variable dt, src/TeaLeaf.jl:69-70).  With the default
+`endtime = 10.0` and the benchmark decks' `end_step` this changes nothing.
+"""
+function TeaLeaf.diffuse!(chunk::B200Chunk, set::Settings)
+    if set.debugfile != "" && isfile(set.debugfile)
+        rm(set.debugfile)
+    end
+    for tt = 1:set.endstep
+        TeaLeaf.debugrecord(set, chunk)
+        rx = set.dtinit / set.dx^2
+        ry = set.dtinit / set.dy^2
+        TeaLeaf.Kernels.haloupdate!(chunk, set, 1, [:energy, :density])
+        error = set.solver.solve!(chunk, set, rx, ry)
+        TeaLeaf.Kernels.solvefinished!(chunk, set)
+        tt % set.summaryfrequency == 0 && TeaLeaf.Kernels.fieldsummary(chunk, set)
+        @info "Timestep $(tt) finished"
+        tt * set.dtinit >= set.endtime && break          # end_time (upstream rule; unused by the reference)
+    end
+    TeaLeaf.Kernels.fieldsummary(chunk, set)
+end
+
 # ---- application entry (src/TeaLeaf.jl:35-44) -----------------------------------------------------
 """
     initialiseapp!(settings; device = 0) -> B200Chunk

@@ -144,5 +144,9 @@ def diffuse(chunk, settings: Settings, geom: HostGeometry, stepwise: bool = Fals
         records.append(rec)
         if on_step:
             on_step(rec)
+        # end_time: parsed by the reference (settings.jl:58) and never used; upstream's rule -- the loop also ends
+        # once the simulated time reaches it.  The timestep is constant (TeaLeaf.jl:69-70).
+        if tt * settings.dtinit >= settings.endtime:
+            break
     final = fieldsummary(chunk, settings, geom)                  # TeaLeaf.jl:82
     return records, final

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libtealeaf_b200.so")
 SOURCES = ["tl_api.cu"]
-DEPS = ["tl_api.cu", "tl_device.cuh", "tl_kernels_basic.cuh", "tl_kernels_fused.cuh", "tl_kernels_ring.cuh", "tl_kernels_persist.cuh", "tl_multi.inl", "tl_eigen.h",
+DEPS = ["tl_api.cu", "tl_device.cuh", "tl_kernels_basic.cuh", "tl_kernels_fused.cuh", "tl_kernels_ring.cuh", "tl_kernels_persist.cuh", "tl_kernels_tma.cuh", "tl_multi.inl", "tl_eigen.h",
         os.path.join("..", "..", "include", "tealeaf_b200.h")]
 
 NVCC_FLAGS = [

@@ -22,6 +22,7 @@
 #include "tl_kernels_fused.cuh"
 #include "tl_kernels_ring.cuh"
 #include "tl_kernels_persist.cuh"
+#include "tl_kernels_tma.cuh"
 #include "tl_eigen.h"
 
 #define TL_MAX_GRID 4096
@@ -117,6 +118,7 @@ struct tl_ctx {
   void *rank_slab[TL_MAX_RANKS]{};   // every other tile's slab, CUDA-IPC mapped (mailboxes; the neighbours' fields)
   bool rank_ipc[TL_MAX_RANKS]{};     // true: mapped with cudaIpcOpenMemHandle (to be closed); false: same-process pointer
   bool comm_ready = false;
+  int prof = 0;             // kernel-boundary micro-profile (option prof, tl_get_option prof_*)
   int use_pdl = 0;          // programmatic dependent launch between the kernels of the iteration loops: measured
                             // SLOWER (profiles/r01d_pdl_sweep.log: 1024^2 CG 24.7 -> 27.6 us/iteration), kept as an option
   int pair_tiled = 1;       // 1: the pair kernels also run on tiles (depth-2 halos, one rendezvous per two iterations / inner steps)
@@ -128,6 +130,9 @@ struct tl_ctx {
   cudaGraphExec_t g_cheby2 = nullptr;
   int g_cheby2_iters = 0;
   int balanced_tiling = 1;  // mid-size tiles: chunk length chosen so that every SM holds exactly two CTAs (compute_tiling)
+  int a_tma = 0;            // 1: kernel A's ring is filled by TMA (cp.async.bulk.tensor boxes + mbarriers, tl_kernels_tma.cuh); measured, off
+  CUtensorMap tma_maps[TMA_NMAPS];
+  bool tma_ready = false;
   int b_ring = 0;           // kernel B flavour: 0 = register batches of 4 rows; 6 / 8 = cp.async ring of that depth (4 / 3 CTAs per SM)
   int cg_persist = 0;       // 1: the CG loop of a single tile runs as ONE persistent cooperative kernel (tl_kernels_persist.cuh)
   PersistSync *psync = nullptr;
@@ -482,6 +487,7 @@ extern "C" void tl_destroy(tl_ctx *c) {
   delete c;
 }
 
+__global__ void k_state_prof(SolveState *st, int on);
 extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   if (TL_IS_MULTI(c)) return multi_all(c, [&](tl_ctx *t, int) { return tl_set_option(t, name, value); });
   if (!c || !name) return TL_ERR_ARG;
@@ -497,8 +503,13 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "hint_stream") c->hint_stream = std::min(std::max(0, (int)value), 2);
   else if (n == "b_reverse") c->b_reverse = value != 0.0;
   else if (n == "comm_fused") c->comm_fused = value != 0.0;
-  else if (n == "use_pdl") c->use_pdl = value != 0.0;
+  else if (n == "use_pdl") c->use_pdl = value != 0.0;   // programmatic dependent launch, released before the kernel tails (tl_pdl_trigger)
   else if (n == "cg_persist") c->cg_persist = value != 0.0;
+  else if (n == "a_tma") {   // 0 off; 1 / 4: TMA ring of 4 row slots; 3: of 3 row slots (two CTAs per SM either way)
+    const int d = (int)value;
+    if (d != 0 && d != 1 && d != 3 && d != 4) return tl_fail(c, TL_ERR_ARG, "a_tma must be 0, 1, 3 or 4");
+    c->a_tma = d == 1 ? 4 : d;
+  }
   else if (n == "balanced_tiling") c->balanced_tiling = value != 0.0;
   else if (n == "cheby_pair") c->cheby_pair = value != 0.0;
   else if (n == "ppcg_pair") c->ppcg_pair = value != 0.0;
@@ -520,6 +531,12 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "pw_chunk_rows") c->pw_chunk_rows = std::max(-1, (int)value);
   else if (n == "graph_iters") c->graph_iters = std::max(1, (int)value);
   else if (n == "use_graph") c->use_graph = value != 0.0;
+  else if (n == "prof") {   // kernel-boundary micro-profile on / off; (re)setting it clears the accumulators
+    cudaSetDevice(c->device);
+    k_state_prof<<<1, 1, 0, c->stream>>>(c->st, value != 0.0);
+    c->prof = value != 0.0;
+    return cudaStreamSynchronize(c->stream) == cudaSuccess ? TL_OK : tl_fail(c, TL_ERR_CUDA, "prof: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   else return tl_fail(c, TL_ERR_ARG, "unknown option %s", name);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
@@ -530,6 +547,12 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   // must never device-synchronise while another tile's kernel waits for them in a rendezvous).
   if (n.rfind("l2_", 0) == 0) return apply_l2_policy(c);
   return TL_OK;
+}
+
+__global__ void k_state_prof(SolveState *st, int on) {
+  st->prof = on;
+  st->prof_start = st->prof_prev_end = 0ull;
+  for (int q = 0; q < 6; q++) st->prof_acc[q] = 0ull;
 }
 
 // Read-back of an option or of a derived quantity (what the tests assert the measured code paths on).
@@ -548,6 +571,7 @@ extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
   else if (n == "comm_fused") v = c->comm_fused;
   else if (n == "use_pdl") v = c->use_pdl;
   else if (n == "cg_persist") v = c->cg_persist;
+  else if (n == "a_tma") v = c->a_tma;
   else if (n == "balanced_tiling") v = c->balanced_tiling;
   else if (n == "cheby_pair") v = c->cheby_pair;
   else if (n == "ppcg_pair") v = c->ppcg_pair;
@@ -572,6 +596,21 @@ extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
   else if (n == "max_grid") v = TL_MAX_GRID;
   else if (n == "num_sms") v = c->num_sms;
   else if (n == "last_cg_phase_ms") v = c->last_cg_ms;   // device time of the CG phase of the last solve
+  else if (n == "prof") v = c->prof;
+  else if (n.rfind("prof_", 0) == 0) {   // averages per profiled kernel, microseconds (SolveState::prof_acc)
+    SolveState h;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(&h, c->st, sizeof h, cudaMemcpyDeviceToHost));
+    const double cnt = (double)h.prof_acc[4], d = cnt > 0 ? cnt * 1e3 : 1.0;
+    if (n == "prof_kernels") v = cnt;
+    else if (n == "prof_body_us") v = h.prof_acc[0] / d;        // kernel entry -> the last block reaches the tail
+    else if (n == "prof_sum_us") v = h.prof_acc[1] / d;         // ticket, partial sums (fence.sys overlapped)
+    else if (n == "prof_xchg_us") v = h.prof_acc[2] / d;        // tile exchange: mailbox stores + wait for the slowest tile
+    else if (n == "prof_gap_us") v = h.prof_acc[3] / d;         // end of the previous kernel's tail -> this kernel's entry
+    else if (n == "prof_fence_us") v = h.prof_acc[5] / d;       // the fence.sys alone
+    else return tl_fail(c, TL_ERR_ARG, "unknown option %s", name);
+  }
   else return tl_fail(c, TL_ERR_ARG, "unknown option %s", name);
   *value = v;
   return TL_OK;
@@ -878,11 +917,23 @@ extern "C" int tl_paint_states(tl_ctx *c, int nstates, const tl_state *states, d
   do { kern<<<(c)->basic_grid, TL_BASIC_THREADS, 0, (c)->stream>>>(__VA_ARGS__);        \
        (c)->launches++; CHECK_LAUNCH(c); } while (0)
 
+// tiles: did a rendezvous of this context time out?  (call with the stream idle; the flag is sticky)
+static int check_comm(tl_ctx *c, const char *where) {
+  if (c->nranks == 1) return TL_OK;
+  SolveState *h = &c->h_st[0];
+  CU(c, cudaMemcpyAsync(h, c->st, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (h->comm_error)
+    return tl_fail(c, TL_ERR_COMM, "%s: tile exchange timed out: tile %d did not hear from tile %d in exchange %llu", where, c->rank,
+                   h->comm_error - 1, h->xseq);
+  return TL_OK;
+}
+
 static int read_scalars(tl_ctx *c, const double *dev, int n, double *out) {
   CU(c, cudaMemcpyAsync(c->h_scal, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < n; i++) out[i] = c->h_scal[i];
-  return TL_OK;
+  return check_comm(c, "all-tiles sum");
 }
 
 static int halo_update_buf(tl_ctx *c, int bufidx, int depth) {
@@ -905,7 +956,7 @@ extern "C" int tl_halo_update(tl_ctx *c, unsigned field_mask, int depth) {
     if (field_mask & (1u << f)) TRY(halo_update_buf(c, buf_index(c, f), depth));
   TRY(tile_barrier(c));  // nobody overwrites an interior a neighbour is still reading
   CU(c, cudaStreamSynchronize(c->stream));
-  return TL_OK;
+  return check_comm(c, "tl_halo_update");
 }
 
 // CG.init! (CG.jl:47-79), asynchronous part: leaves rro in st->red_rr (all-reduced).
@@ -1147,9 +1198,57 @@ static int launch_ring(tl_ctx *c, const CgAParams &P) {
   CU(c, tl_launch(c, k_cg_fused_w_ring<U, S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
 }
+// ---- TMA flavour of kernel A (option a_tma): one 2-D tensor map per buffer, encoded once per context ----
+typedef CUresult (*tl_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int tma_prepare(tl_ctx *c) {
+  if (c->tma_ready) return TL_OK;
+  static tl_encode_tiled_fn encode = nullptr;
+  if (!encode) {   // the driver entry point, without linking libcuda
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CU(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return tl_fail(c, TL_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    encode = (tl_encode_tiled_fn)fn;
+  }
+  const int bufs[TMA_NMAPS] = {TL_R, TL_P, B_P1, TL_KY, TL_KX, TL_U};
+  for (int q = 0; q < TMA_NMAPS; q++) {
+    // the whole padded buffer: dim0 = the padded row (pitch doubles), dim1 = rows incl. halos; box = 68 x 1
+    void *base = (double *)c->slab + (size_t)bufs[q] * c->buf_doubles;
+    const cuuint64_t dims[2] = {(cuuint64_t)c->g.pitch, (cuuint64_t)c->rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)c->g.pitch * sizeof(double)};
+    const cuuint32_t box[2] = {TL_TMA_BOX, 1}, estr[2] = {1, 1};
+    const CUresult r = encode(&c->tma_maps[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return tl_fail(c, TL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for buffer %d", (int)r, bufs[q]);
+  }
+  c->tma_ready = true;
+  return TL_OK;
+}
+template <bool U, int S, int MINB>
+static int launch_cg_a_tma(tl_ctx *c, const CgAParams &A) {
+  TRY(tma_prepare(c));
+  CgATmaParams P;
+  P.a = A;
+  memcpy(P.maps, c->tma_maps, sizeof P.maps);
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_TMA_STAGE_BYTES;
+  static unsigned long long prepared = 0;
+  TRY(tl_prepare_smem(c, k_cg_fused_w_tma<U, S, MINB>, smem, &prepared));
+  CU(c, tl_launch(c, k_cg_fused_w_tma<U, S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
+  return TL_OK;
+}
+
 template <bool U>
 static int launch_cg_a(tl_ctx *c) {
   const CgAParams P = cg_a_params(c);
+  if (c->a_tma) {
+    if (c->a_tma == 3) TRY((launch_cg_a_tma<U, 3, 2>(c, P)));
+    else TRY((launch_cg_a_tma<U, 4, 2>(c, P)));
+    CHECK_LAUNCH(c);
+    return TL_OK;
+  }
   switch (c->ring_eff) {
     case 3: TRY((launch_ring<U, 3, 3>(c, P))); break;
     case 4: TRY((launch_ring<U, 4, 2>(c, P))); break;

@@ -76,6 +76,12 @@ struct SolveState {
   // tile_barrier(): an out-of-place all-tiles sum of `barrier_zero` (never written: stays 0.0) into
   // `barrier_out`, so that a rendezvous never accumulates into a slot somebody else uses
   double barrier_zero, barrier_out;
+  // micro-profile of the kernel boundaries (option "prof"; tl_get_option "prof_*"): globaltimer stamps taken by
+  // block 0 at kernel entry and by the LAST block around the grid sum, the fence.sys and the tile exchange
+  int prof, pad2;
+  unsigned long long prof_start, prof_prev_end;
+  unsigned long long prof_acc[6];   // ns: [0] entry -> last block in the tail, [1] ticket + partial sums, [2] tile exchange,
+                                    //     [3] previous kernel's end -> this entry (launch gap), [4] kernels counted, [5] fence.sys
 };
 
 // ---- multi-GPU: peer-mapped mailboxes and halo push targets --------------------------------
@@ -110,12 +116,29 @@ __host__ __device__ inline bool tl_should_stop(int it, double rr, const StopCfg 
 
 #ifdef __CUDACC__
 
-// Programmatic dependent launch: let the next kernel of the stream become resident right away,
-// then wait until the previous one has completed and its writes are visible.  Both instructions
-// are no-ops for a kernel launched without the programmatic attribute.
+// Programmatic dependent launch (option use_pdl; both instructions are no-ops for a kernel launched without the
+// programmatic attribute).  Mode 1 (round 1, measured slower): the dependents are released at kernel ENTRY, become
+// resident at once and spin in griddepcontrol.wait next to the running CTAs.  Mode 2: the release is issued by every CTA
+// when its rows are done, just before the kernel tail (tl_pdl_trigger) -- the next kernel's CTAs are scheduled into the
+// slots that free up while the last block sums the partials and meets the other tiles, and the launch gap between two
+// dependent kernels overlaps the tail.  Either way a dependent waits (griddepcontrol.wait) until the predecessor has
+// completed and its writes are visible before it reads anything.
 __device__ __forceinline__ void tl_pdl_entry() {
+#ifdef TL_PDL_EARLY
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void tl_pdl_trigger() {
+#ifndef TL_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+__device__ __forceinline__ unsigned long long tl_globaltimer();
+// Kernel-entry stamp of the boundary micro-profile (SolveState::prof); free when profiling is off.
+__device__ __forceinline__ void tl_prof_entry(SolveState *st) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && st->prof) *(volatile unsigned long long *)&st->prof_start = tl_globaltimer();
 }
 
 __device__ __forceinline__ double tl_warp_sum(double v) {
@@ -147,7 +170,7 @@ __device__ __forceinline__ double tl_block_sum(double v, double *sm) {
 // are run-to-run reproducible.  `NV` values are reduced at once.
 template <int NV>
 __device__ __forceinline__ bool tl_grid_sum(double (&v)[NV], double *partials, unsigned *counter, double *sm,
-                                            bool sys_fence = false) {
+                                            bool sys_fence = false, unsigned long long *prof_fence_ns = nullptr) {
   __shared__ bool s_last;
 #pragma unroll
   for (int q = 0; q < NV; q++) {
@@ -164,11 +187,34 @@ __device__ __forceinline__ bool tl_grid_sum(double (&v)[NV], double *partials, u
   __threadfence();
   // tiles exchange after this sum: one thread makes everything this GPU wrote (the halo pushes
   // of all blocks, ordered before their tickets) visible system-wide while the others add up
-  if (sys_fence && threadIdx.x == blockDim.x - 1) __threadfence_system();
+  if (sys_fence && threadIdx.x == blockDim.x - 1) {
+    if (prof_fence_ns) {
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+      __threadfence_system();
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      *prof_fence_ns += t1 - t0;
+    } else {
+      __threadfence_system();
+    }
+  }
+  // Partials in batches of 8 INDEPENDENT L2 loads per thread, added in the same fixed order as a plain strided loop
+  // (a dependent load-add chain over 4096 partials cost ~5 us of every kernel: profiles/r02d_boundary_profile_n2.jsonl).
 #pragma unroll
   for (int q = 0; q < NV; q++) {
     double t = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += __ldcg(&partials[(size_t)q * gridDim.x + b]);
+    const double *pq = partials + (size_t)q * gridDim.x;
+    for (unsigned base = 0; base < gridDim.x; base += 8u * blockDim.x) {
+      double pv[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const unsigned b = base + k * blockDim.x + threadIdx.x;
+        pv[k] = b < gridDim.x ? __ldcg(pq + b) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) t += pv[k];
+    }
     v[q] = tl_block_sum(t, sm);
   }
   if (threadIdx.x == 0) *counter = 0u;
@@ -249,9 +295,13 @@ __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState
 // in thread 0 of the last block, with acc[0] = the (global) total.
 __device__ __forceinline__ bool tl_kernel_tail(double (&acc)[1], bool do_sum, SolveState *st, double *partials,
                                                const CommDev *cd, double *sm) {
+  const bool prof = st->prof != 0;
+  unsigned long long t_in = 0;
+  if (prof && threadIdx.x == 0) t_in = tl_globaltimer();
+  tl_pdl_trigger();   // this CTA's rows are done: the next kernel of the stream may be scheduled (it waits for our completion)
   bool last;
   if (do_sum) {
-    last = tl_grid_sum<1>(acc, partials, &st->counter, sm, cd != nullptr);
+    last = tl_grid_sum<1>(acc, partials, &st->counter, sm, cd != nullptr, prof ? &st->prof_acc[5] : nullptr);
   } else {
     __shared__ bool s_last_nosum;
     __syncthreads();
@@ -259,7 +309,9 @@ __device__ __forceinline__ bool tl_kernel_tail(double (&acc)[1], bool do_sum, So
       __threadfence();
       s_last_nosum = (atomicAdd(&st->counter, 1u) == gridDim.x - 1);
       if (s_last_nosum) {
+        const unsigned long long tf = prof ? tl_globaltimer() : 0;
         if (cd) __threadfence_system(); else __threadfence();
+        if (prof) st->prof_acc[5] += tl_globaltimer() - tf;
         st->counter = 0u;
       }
     }
@@ -268,7 +320,19 @@ __device__ __forceinline__ bool tl_kernel_tail(double (&acc)[1], bool do_sum, So
     acc[0] = 0.0;
   }
   if (!last) return false;
+  unsigned long long t_sum = 0;
+  if (prof && threadIdx.x == 0) t_sum = tl_globaltimer();
   if (cd) acc[0] = tl_tile_exchange(cd, st, acc[0], sm);
+  if (prof && threadIdx.x == 0) {
+    const unsigned long long t_end = tl_globaltimer();
+    const unsigned long long t_start = *(volatile unsigned long long *)&st->prof_start;
+    if (t_start && t_in > t_start) st->prof_acc[0] += t_in - t_start;
+    st->prof_acc[1] += t_sum - t_in;
+    st->prof_acc[2] += t_end - t_sum;
+    if (st->prof_prev_end && t_start > st->prof_prev_end) st->prof_acc[3] += t_start - st->prof_prev_end;
+    st->prof_prev_end = t_end;
+    st->prof_acc[4] += 1;
+  }
   return threadIdx.x == 0;
 }
 

@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBPar
   tl_pdl_entry();
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int it = st->iter;
   const double rr_cur = st->red_rr;
   if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_ppcg_ur_sd(const PpcgUr
   tl_pdl_entry();
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int it = st->iter;
   const double rr_cur = st->red_rr;
   if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;

@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int it = st->iter;
   const double rr_cur = st->red_rr;
   if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_r_ring(cons
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int it = st->iter;
   const double rr_cur = st->red_rr;
   if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
@@ -366,6 +368,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int step = st->cheby_step;
   double alpha = 0.0, beta = 0.0;
   bool calc_norm, store_wr;
@@ -497,6 +500,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_ring(cons
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int step = st->cheby_step;
   if (st->comm_error || tl_cheby_should_stop(*st)) return;
   const int ttA = st->cheby_tt0 + step - 1;
@@ -629,6 +633,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_pair_ring(const
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int it = st->iter;
   if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
   const int pp = st->inner_pp;
@@ -744,6 +749,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(cons
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int it = st->iter;
   if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
   const int pp = st->inner_pp;
@@ -834,6 +840,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_dk(const 
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int it = st->iter;
   if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
   const int pp = st->inner_pp, n = st->inner_steps, k = P.k;
@@ -945,6 +952,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_jacobi_fused_ring(co
   extern __shared__ __align__(128) unsigned char ring_raw[];
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int it = st->iter;
   if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
   const double *__restrict__ uin = (it & 1) ? P.ub : P.ua;
@@ -1027,6 +1035,7 @@ __global__ void __launch_bounds__(TL_BASIC_THREADS) k_jacobi_resid(const JacobiP
   tl_pdl_entry();
   __shared__ double sm[32];
   SolveState *st = P.st;
+  tl_prof_entry(st);
   const int it = st->iter;
   if (st->comm_error) return;
   if (!P.force_resid && (it == 0 || it % 50 != 0)) return;

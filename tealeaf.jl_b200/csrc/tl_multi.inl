@@ -63,12 +63,15 @@ static int multi_run(tl_ctx *c, const std::function<int(int)> &job) {
     m->cv_job.notify_all();
     m->cv_done.wait(lk, [&] { return m->pending == 0; });
   }
+  int first = TL_OK;
+  std::string all;
   for (int i = 0; i < m->n; i++)
-    if (m->rc[i] != TL_OK) {
-      c->err = "tile " + std::to_string(i) + ": " + (m->tiles[i] ? m->tiles[i]->err : std::string("not created"));
-      return m->rc[i];
+    if (m->rc[i] != TL_OK) {      // every failing tile's own story (a rendezvous failure is only understood from all of them)
+      if (first == TL_OK) first = m->rc[i];
+      all += (all.empty() ? "" : "; ") + ("tile " + std::to_string(i) + ": ") + (m->tiles[i] ? m->tiles[i]->err : std::string("not created"));
     }
-  return TL_OK;
+  if (first != TL_OK) c->err = all;
+  return first;
 }
 
 template <typename F>

@@ -373,6 +373,29 @@ def test_persistent_cg_is_bit_identical(nx, ny, solver, over):
         assert max(b[6]) < min(a[6])          # one launch for the whole loop instead of two per iteration
 
 
+@pytest.mark.parametrize("slots", [3, 4])
+@pytest.mark.parametrize("nx,ny,solver,over", [(200, 120, "cg", {}), (257, 19, "cg", {}), (1, 40, "cg", {}), (63, 64, "cg", {}), (64, 5, "cg", {}),
+                                              (700, 523, "cg", {"maxiters": 400}), (2048, 1536, "cg", {"maxiters": 120}),
+                                              (96, 160, "ppcg", {"ppcginnersteps": 6}), (129, 70, "cg", {"halodepth": 3})])
+def test_kernel_a_tma_is_bit_identical(nx, ny, solver, over, slots):
+    """Option a_tma: kernel A with its row ring filled by TMA (cp.async.bulk.tensor 68 x 1 boxes, mbarrier per ring slot,
+    one elected lane issues; tl_kernels_tma.cuh) -- same rows, same arithmetic, same summation order as the cp.async ring."""
+    outs = []
+    for d in (0, slots):
+        s = classic_settings(nx, ny=ny, steps=2, solver=solver, **over)
+        chunk, geom = tl.initialiseapp(s, backend=_device())
+        chunk.set_option("a_tma", d)
+        recs, final = tl.diffuse(chunk, s, geom)
+        outs.append(([r["iters"] for r in recs], [r["error"] for r in recs], final["temp"],
+                     {f: chunk.get_field(f) for f in ("u", "energy", "p", "r", "w")}, chunk.cgalpha.copy()))
+        chunk.close()
+    a, b = outs
+    assert a[:3] == b[:3], (a[:3], b[:3])
+    for f in a[3]:
+        np.testing.assert_array_equal(a[3][f], b[3][f], err_msg=f)
+    np.testing.assert_array_equal(a[4], b[4])
+
+
 @pytest.mark.parametrize("depth", [6, 8])
 @pytest.mark.parametrize("nx,ny", [(200, 120), (257, 19), (1, 40), (700, 523)])
 def test_kernel_b_ring_is_bit_identical(nx, ny, depth):

@@ -139,3 +139,55 @@ def test_solveinfo_struct_mirrors_tl_solve_info():
             hdr.append((n, c_class(tname + " x")))
     assert jl == hdr, (jl, hdr)
     assert [(n, lp64(c)) for n, c in jl] == [(n, lp64(ctypes_class(t))) for n, t in lib.SolveInfo._fields_]
+
+
+def _strip_julia(text):
+    """drop docstrings / strings / comments (identifiers inside them are not code)"""
+    text = re.sub(r'"""(.|\n)*?"""', '""', text)
+    text = re.sub(r'"(\\.|[^"\\\n])*"', '""', text)
+    return "\n".join(line.split("#", 1)[0] for line in text.splitlines())
+
+
+def test_no_unexported_reference_name_is_used_unqualified():
+    """`using TeaLeaf` only brings the reference's EXPORTED names into scope (src/chunk.jl:4-7, src/settings.jl:4-8,
+    src/TeaLeaf.jl:2); anything else the binding takes from the reference must be written `TeaLeaf.name` (or imported
+    explicitly), otherwise the first call throws UndefVarError -- which no test here could notice, Julia being absent.
+    The name lists come from the reference tree (tests/golden/make_reference_names.py)."""
+    import json
+    names = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_names.json"), encoding="utf-8"))
+    in_scope = set(names["using_TeaLeaf"])
+    code = _strip_julia(JL)
+    in_scope |= {n.strip() for m in re.finditer(r"using\s+TeaLeaf(?:\.\w+)*\s*:\s*(.*)", code) for n in m.group(1).split(",")}
+    in_scope |= {n.strip() for m in re.finditer(r"using\s+\.\.TeaLeafB200\s*:\s*(.*)", code) for n in m.group(1).split(",")}
+    # names the binding defines itself (functions, structs, modules, consts) -- unqualified definitions only
+    local = set(re.findall(r"^\s*function\s+([A-Za-z_][\w!]*)\s*\(", code, flags=re.M))
+    local |= set(re.findall(r"^\s*(?:mutable\s+)?struct\s+([A-Za-z_]\w*)", code, flags=re.M))
+    local |= set(re.findall(r"^\s*module\s+([A-Za-z_]\w*)", code, flags=re.M))
+    local |= set(re.findall(r"^\s*const\s+([A-Za-z_]\w*)", code, flags=re.M))
+    local |= set(re.findall(r"^\s*([A-Za-z_][\w!]*)\([^=\n]*\)\s*=(?!=)", code, flags=re.M))
+    offenders = []
+    for m in re.finditer(r"(?<![\w.:!])([A-Za-z_][\w!]*)", code):
+        name = m.group(1)
+        if name in names["defined"] and name not in in_scope and name not in local:
+            line = code[:m.start()].count("\n") + 1
+            offenders.append((name, line))
+    assert not offenders, f"non-exported reference names used unqualified (write TeaLeaf.<name>): {offenders}"
+    # and the qualified uses must name things the reference really defines
+    for m in re.finditer(r"TeaLeaf\.(?:Kernels\.|CG\.|Cheby\.|PPCG\.|Jacobi\.)?([A-Za-z_][\w!]*)", code):
+        if m.group(1) not in ("Kernels", "TeaLeafB200"):
+            assert m.group(1) in names["defined"], f"TeaLeaf.{m.group(1)} does not exist in the reference"
+
+
+def test_reference_names_fixture_is_current():
+    """When the reference tree is present (this container), the committed fixture must match it."""
+    import json
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/src"):
+        import pytest
+        pytest.skip("reference tree not present (GPU box)")
+    path = os.path.join(ROOT, "tests", "golden", "reference_names.json")
+    before = json.load(open(path, encoding="utf-8"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_reference_names.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert json.load(open(path, encoding="utf-8")) == before

@@ -34,9 +34,10 @@ def test_multi_context_solves_match_oracle(solver, n, px, py, nx, ny, over):
     ora = run(_oracle(), s())
     assert_parity(dev, ora, iter_slack=1 if solver == "cg" else 0)
     # the gathered global arrays carry the physical halos too (reflected u)
-    u = dev[0].get_field("u")
-    np.testing.assert_array_equal(u[1, 2:-2], u[2, 2:-2])
-    np.testing.assert_array_equal(u[2:-2, -2], u[2:-2, -3])
+    if solver == "cg":       # CG keeps the halo of u reflected (haloupdate!(u, p), CG.jl:22)
+        u = dev[0].get_field("u")
+        np.testing.assert_array_equal(u[1, 2:-2], u[2, 2:-2])
+        np.testing.assert_array_equal(u[2:-2, -2], u[2:-2, -3])
     dev[0].close()
 
 

@@ -207,3 +207,21 @@ def test_jacobi_oracle_matches_numpy_twin_and_converges_towards_cg():
     a, b = interior(c4.get_field("u")), interior(c5.get_field("u"))
     assert np.abs(a - b).max() / np.abs(b).max() < 1e-12
 
+
+
+def test_end_time_ends_the_timestep_loop():
+    """`end_time` (settings.jl:58: parsed, never used by the reference) ends the loop once tt * dt reaches it, as
+    upstream does; with the default 10.0 the decks' `end_step` decides."""
+    import tealeaf_jl_b200 as tl
+    from tealeaf_jl_b200.decks import CLASSIC_DECK
+    from oracle.oracle import OracleChunk
+    deck = CLASSIC_DECK.format(nx=24, ny=24, steps=10, solver="cg").replace("end_step=10", "end_step=10\nend_time=0.012")
+    s = tl.parse_settings_text(deck)
+    assert s.endtime == 0.012 and s.endstep == 10
+    chunk, geom = tl.initialiseapp(s, backend=OracleChunk)
+    recs, final = tl.diffuse(chunk, s, geom)
+    assert len(recs) == 3                      # 3 * 0.004 >= 0.012
+    s2 = tl.parse_settings_text(CLASSIC_DECK.format(nx=24, ny=24, steps=3, solver="cg"))
+    chunk2, geom2 = tl.initialiseapp(s2, backend=OracleChunk)
+    recs2, final2 = tl.diffuse(chunk2, s2, geom2)
+    assert [r["iters"] for r in recs] == [r["iters"] for r in recs2] and final["temp"] == final2["temp"]

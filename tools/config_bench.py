@@ -19,7 +19,6 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ALG_BYTES = {"cg": 104, "cheby": 88}   # per cell-iteration; PPCG: 128 outer + 80 per inner step
 
@@ -38,6 +37,8 @@ def main():
     ap.add_argument("--comm", default="fused,nccl")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--opt", action="append", default=[], help="tl_set_option name=value (repeatable)")
+    ap.add_argument("--prof", action="store_true",
+                    help="kernel-boundary micro-profile (globaltimer stamps in the kernel tails): averages per kernel in the JSON line")
     args = ap.parse_args()
 
     import torch
@@ -85,6 +86,20 @@ def main():
             info = solver.solve(chunk, s, rx, ry)
             if best is None or info["solve_ms"] < best["solve_ms"]:
                 best = info
+        prof = None
+        if args.prof:      # one more solve with the stamps on (they cost a few globaltimer reads per kernel)
+            chunk.set_option("prof", 1)
+            chunk.copy_field("energy", "energy0")
+            tl.haloupdate(chunk, s, 1, ["energy", "density"])
+            pinfo = solver.solve(chunk, s, rx, ry)
+            prof = {k: chunk.get_option("prof_" + k) for k in ("kernels", "body_us", "sum_us", "xchg_us", "gap_us", "fence_us")}
+            prof["solve_ms_with_stamps"] = pinfo["solve_ms"]
+            chunk.set_option("prof", 0)
+            if dist is not None:
+                allp = [None] * world
+                dist.all_gather_object(allp, prof)
+                prof = {"rank0": allp[0], "max_over_ranks": {k: max(p[k] for p in allp) for k in prof},
+                        "min_over_ranks": {k: min(p[k] for p in allp) for k in prof}}
         ms = best["solve_ms"]
         if dist is not None:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -107,6 +122,7 @@ def main():
                 "us_per_sweep": 1e3 * ms / max(work_iters, 1),
                 "algorithmic_gbs_per_gpu": alg / (ms * 1e-3) / 1e9 / world,
                 "kernel_launches": best["kernel_launches"],
+                **({"boundary_profile_us_per_kernel": prof} if prof else {}),
             }), flush=True)
         chunk.close()
     if dist is not None:
