@@ -341,6 +341,7 @@ static void destroy_graphs(tl_ctx *c) {
 template <typename F> static int multi_all(tl_ctx *c, F fn);                         // fn(tile, idx) on every tile, concurrently
 template <typename F> static int multi_scalar(tl_ctx *c, double *out, F fn);         // fn(tile, &v): the all-tiles value
 template <typename F> static int multi_max(tl_ctx *c, double *out, F fn);            // fn(tile, &v): max over tiles
+template <typename F> static int multi_min(tl_ctx *c, double *out, F fn);            // fn(tile, &v): min over tiles
 template <typename F> static int multi_solve(tl_ctx *c, tl_solve_info *info, F fn);  // fn(tile, &info, idx)
 static void multi_destroy(tl_ctx *c);
 static int multi_set_field(tl_ctx *c, int field, const double *host, long ld);
@@ -557,7 +558,10 @@ __global__ void k_state_prof(SolveState *st, int on) {
 
 // Read-back of an option or of a derived quantity (what the tests assert the measured code paths on).
 extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
-  if (TL_IS_MULTI(c)) return multi_max(c, value, [&](tl_ctx *t, double *o) { return tl_get_option(t, name, o); });
+  if (TL_IS_MULTI(c)) {
+    if (name && strncmp(name, "debug_", 6) == 0) return multi_min(c, value, [&](tl_ctx *t, double *o) { return tl_get_option(t, name, o); });
+    return multi_max(c, value, [&](tl_ctx *t, double *o) { return tl_get_option(t, name, o); });
+  }
   if (!c || !name || !value) return TL_ERR_ARG;
   const std::string n(name);
   double v;
@@ -596,6 +600,21 @@ extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
   else if (n == "max_grid") v = TL_MAX_GRID;
   else if (n == "num_sms") v = c->num_sms;
   else if (n == "last_cg_phase_ms") v = c->last_cg_ms;   // device time of the CG phase of the last solve
+  else if (n == "debug_comm_table_ok") {   // does the device copy of the mailbox table still hold what tl_comm_connect wrote?
+    v = 1.0;
+    if (c->nranks > 1 && c->comm_ready) {
+      CommDev h;
+      CU(c, cudaSetDevice(c->device));
+      CU(c, cudaMemcpyAsync(c->h_scal, c->d_comm, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+      memcpy(&h, c->h_scal, sizeof h);
+      if (h.nranks != c->nranks || h.rank != c->rank) v = 0.0;
+      for (int r = 0; r < c->nranks; r++) {
+        const MailSlot *want = (r == c->rank) ? c->mail : (MailSlot *)((char *)c->rank_slab[r] + c->rank_blob[r].mail_offset);
+        if (h.mail[r] != want) v = 0.0;
+      }
+    }
+  }
   else if (n == "prof") v = c->prof;
   else if (n.rfind("prof_", 0) == 0) {   // averages per profiled kernel, microseconds (SolveState::prof_acc)
     SolveState h;
@@ -682,7 +701,16 @@ extern "C" int tl_comm_connect(tl_ctx *c, const void *all_blobs, const void *id1
     }
     hd.mail[r] = (MailSlot *)((char *)c->rank_slab[r] + blobs[r].mail_offset);
   }
-  CU(c, cudaMemcpy(c->d_comm, &hd, sizeof hd, cudaMemcpyHostToDevice));
+  // the table goes up on the context's OWN stream (a synchronous cudaMemcpy from pageable memory runs on the legacy
+  // default stream, which the non-blocking solver stream is not ordered with, and may return before its DMA has landed)
+  static_assert(sizeof(CommDev) <= 64 * sizeof(double), "CommDev must fit the pinned scratch");
+  if (getenv("TL_COMM_TABLE_LEGACY")) {
+    CU(c, cudaMemcpy(c->d_comm, &hd, sizeof hd, cudaMemcpyHostToDevice));
+  } else {
+    memcpy(c->h_scal, &hd, sizeof hd);
+    CU(c, cudaMemcpyAsync(c->d_comm, c->h_scal, sizeof hd, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
   for (int r = 0; r < c->nranks; r++) c->rank_blob[r] = blobs[r];
   for (int s = 0; s < 4; s++) {
     const int nr = c->nbr_rank[s];

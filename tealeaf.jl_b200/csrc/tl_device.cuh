@@ -258,15 +258,20 @@ __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState
     st->xseq = s_seq;
   }
   __syncthreads();
-  const int n = cd->nranks;
+  // The mailbox table is read with strong (L1-bypassing, system-scope) loads: it was written by a host copy, possibly
+  // into memory that held an older context's table, and a stale cached pointer would send a packet astray.
+  const int n = (int)tl_ld_relaxed_sys((const unsigned long long *)&cd->nranks) ;   // {nranks, rank} share one 8-byte word
+  const int my_rank = (int)(tl_ld_relaxed_sys((const unsigned long long *)&cd->nranks) >> 32);
   const unsigned seq = (unsigned)s_seq;
   const int par = (int)(seq & 1u);
   if ((int)threadIdx.x < n) {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(sm[0]);
-    MailSlot *dst = cd->mail[threadIdx.x] + par * TL_MAX_RANKS + cd->rank;
-    tl_st_relaxed_sys(&dst->lo, ((unsigned long long)seq << 32) | (bits & 0xffffffffull));
-    tl_st_relaxed_sys(&dst->hi, ((unsigned long long)seq << 32) | (bits >> 32));
-    const MailSlot *src = cd->mail[cd->rank] + par * TL_MAX_RANKS + threadIdx.x;
+    const unsigned long long w_lo = ((unsigned long long)seq << 32) | (bits & 0xffffffffull);
+    const unsigned long long w_hi = ((unsigned long long)seq << 32) | (bits >> 32);
+    MailSlot *dst = (MailSlot *)tl_ld_relaxed_sys((const unsigned long long *)&cd->mail[threadIdx.x]) + par * TL_MAX_RANKS + my_rank;
+    tl_st_relaxed_sys(&dst->lo, w_lo);
+    tl_st_relaxed_sys(&dst->hi, w_hi);
+    const MailSlot *src = (const MailSlot *)tl_ld_relaxed_sys((const unsigned long long *)&cd->mail[my_rank]) + par * TL_MAX_RANKS + threadIdx.x;
     unsigned long long lo, hi;
     unsigned spins = 0;
     unsigned long long t0 = 0;
@@ -278,12 +283,18 @@ __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState
         const unsigned long long t = tl_globaltimer();
         if (t0 == 0) t0 = t;
         else if (t - t0 > TL_XCHG_TIMEOUT_NS) { st->comm_error = 1 + (int)threadIdx.x; break; }   // 1 + the rank not heard from
+        // the packet is idempotent (same exchange number, same value): post it again while waiting
+        dst = (MailSlot *)tl_ld_relaxed_sys((const unsigned long long *)&cd->mail[threadIdx.x]) + par * TL_MAX_RANKS + my_rank;
+        tl_st_relaxed_sys(&dst->lo, w_lo);
+        tl_st_relaxed_sys(&dst->hi, w_hi);
       }
     }
     sm[1 + threadIdx.x] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    // acquire side, by the threads that observed the slots: later reads (the next kernel's halo loads) see the
+    // neighbours' pushes that were ordered before those slots
+    __threadfence_system();
   }
   __syncthreads();
-  __threadfence_system();   // acquire side: later reads (the next kernel's halo loads) see the neighbours' pushes
   double total = 0.0;
   if (threadIdx.x == 0)
     for (int r = 0; r < n; r++) total += sm[1 + r];

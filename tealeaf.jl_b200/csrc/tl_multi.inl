@@ -116,6 +116,16 @@ static int multi_solve(tl_ctx *c, tl_solve_info *info, F fn) {
   return rc;
 }
 
+// fn(tile, &value): the minimum over the tiles (health checks)
+template <typename F>
+static int multi_min(tl_ctx *c, double *out, F fn) {
+  Multi *m = c->multi;
+  std::vector<double> tmp(m->n, 0.0);
+  const int rc = multi_run(c, [&](int i) { return fn(m->tiles[i], &tmp[i]); });
+  if (rc == TL_OK && out) *out = *std::min_element(tmp.begin(), tmp.end());
+  return rc;
+}
+
 static int multi_tile_offset(const tl_ctx *c, int idx, int *x0, int *y0) {
   *x0 = c->multi->x0[idx];
   *y0 = c->multi->y0[idx];
