@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+JSON_OUT = sys.stdout      # main() replaces it by a private duplicate of the original stdout
 METRIC = "solver cell-iterations/sec"
 UNIT = "cell-iterations/s"
 CG_ALG_BYTES = 104          # w! 32 + ur! 48 + p! 24 bytes per cell-iteration
@@ -52,6 +53,11 @@ def _load_traffic():
 
 
 TRAFFIC = _load_traffic()     # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed kernel@NXxNY
+
+
+def _emit(line):
+    JSON_OUT.write(line + "\n")
+    JSON_OUT.flush()
 
 
 def measured_peaks():
@@ -183,7 +189,7 @@ def run_reference(args):
     chunk1.close()
     serial = n * n * serial_iters / t1
     sample = f"{iters} CG iterations per step of the {n}x{n} classic deck (w!, ur!, p!, halo), OpenMP oracle, {threads} threads"
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -511,7 +517,7 @@ def run_b200(args):
         cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "N>1: measured at N=1 only"}
 
     if rank == 0:
-        print(json.dumps({
+        _emit(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -551,7 +557,13 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-legs", action="store_true", help="skip other_configs (configs[2]/[3] and the weak base tile)")
     args = ap.parse_args()
-    # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+    # stdout carries exactly ONE JSON line.  Whatever else the process and its libraries print (NCCL's version banner
+    # went to stdout in spite of NCCL_DEBUG_FILE on some boxes) is sent to stderr: file descriptor 1 is pointed at
+    # stderr for the whole run and the JSON line is written to a private duplicate of the original stdout.
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         from oracle import oracle as _o      # the CPU arm never builds or loads the CUDA library

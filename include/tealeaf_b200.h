@@ -103,20 +103,29 @@ int tl_abi_version(void);
  *   graph_iters, use_graph      iterations per CUDA graph launch (8) / plain launches instead
  *   b_reverse                   kernel B walks the tile top-down (1)
  *   b_ring                      kernel B flavour: 0 register batches (default), 6 / 8 cp.async ring
+ *   a_tma                       kernel A's row ring filled by TMA (cp.async.bulk.tensor + mbarriers): 0 off (default: measured,
+ *                               not faster), 3 / 4 ring slots
  *   cg_persist                  1: the CG loop of a single tile as ONE persistent cooperative kernel
- *   cheby_pair, ppcg_pair       single tile: two Chebyshev iterations / PPCG inner steps per pass (default 1)
+ *   cheby_pair, ppcg_pair       two Chebyshev iterations / PPCG inner steps per pass (temporal blocking; default 1)
+ *   pair_tiled                  the pair kernels also on tiles: depth-2 halos, one exchange per two iterations (default 1)
  *   pair_rows                   rows per warp task of the pair kernels (32)
- *   pair_tiled                  EXPERIMENTAL, default 0, not yet run on a GPU: Chebyshev pairs on tiles (one exchange per two iterations)
  *   balanced_tiling             mid-size tiles: chunk length that puts exactly two CTAs on every SM (default 1)
  *   hint_keep, hint_stream, l2_persist_mb, l2_hit_scale, l2_persist_field    L2 policy experiments
- *   use_pdl                     programmatic dependent launch between the loop kernels
+ *   use_pdl                     programmatic dependent launch between the loop kernels, released before the kernel tails
  *   comm_fused                  tiles: 1 halo pushes + mailbox sums inside the kernels (default), 0 NCCL + pull kernels
- *   ppcg_halo_depth             tiles: exchange every k PPCG inner steps (0 = halo_depth)
+ *   ppcg_halo_depth             tiles, one kernel per inner step: exchange every k steps (0 = automatic: the pair kernels,
+ *                               i.e. every 2 steps, or every halo_depth steps when they are off)
+ *   prof                        kernel-boundary micro-profile: globaltimer stamps in the kernel tails; read the averages per
+ *                               kernel (microseconds) with tl_get_option: prof_kernels, prof_body_us (entry -> last block in
+ *                               the tail), prof_sum_us (ticket + partial sums), prof_fence_us (fence.sys), prof_xchg_us (tile
+ *                               exchange), prof_gap_us (previous tail -> next entry; kernels without a tail count as gap)
  * Unknown names return TL_ERR_ARG. */
 int tl_set_option(tl_ctx *ctx, const char *name, double value);
 /* Read-back of any option above, and of derived quantities: ring_stages_effective (the ring depth in use),
  * rows_per_chunk / pw_rows_per_chunk / pair_rows_per_chunk and fused_grid / pw_grid / pair_grid (how the tile
- * is cut into warp tasks and CTAs), max_grid (the bound on a grid: the partials array), num_sms. */
+ * is cut into warp tasks and CTAs), max_grid (the bound on a grid: the partials array), num_sms, last_cg_phase_ms
+ * (device time of the CG phase -- preamble, CG presteps, flush -- of the last Chebyshev / PPCG solve), prof_* (above).
+ * On a tl_create_multi context: the maximum over the tiles. */
 int tl_get_option(tl_ctx *ctx, const char *name, double *value);
 
 /* ---- multi-GPU wiring (no counterpart in the reference: it has a single Chunk) ---- */

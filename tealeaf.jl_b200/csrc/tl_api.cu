@@ -125,6 +125,7 @@ struct tl_ctx {
   int ppcg_pair = 1;        // 1: PPCG inner steps run two per pass (k_ppcg_pair_ring; an odd count ends with one single step)
   int cheby_pair = 1;       // 1: reduction-free Chebyshev iterations run two per pass (k_cheby_pair_ring)
   int pair_rows = 32;       // rows per warp task of the pair kernel (two redundant rows per task)
+  int pair_stages = 4;      // cp.async ring depth of the pair kernels: 4 (default) or 5, two CTAs per SM either way
   Tiling pair_tiling{};
   int pair_grid = 0;
   cudaGraphExec_t g_cheby2 = nullptr;
@@ -168,11 +169,19 @@ static cudaError_t tl_launch(tl_ctx *c, void (*kern)(const P), int grid, int blo
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember which devices a
 // kernel instantiation has been prepared on (one static mask per instantiation).
+// Experiment, off (process-wide, as kernel attributes are): TEALEAF_B200_CARVEOUT=1 makes every loop kernel ask for the
+// all-shared L1 / shared-memory split, so that consecutive kernels never make the SMs reconfigure.  Measured on 2 GPUs
+// (profiles/r02i_carveout_acquire_ab_n2.jsonl): the launch gap does not shrink (3.2 vs 3.0 us) and the kernel bodies slow down
+// by 10-16 % (28 KB of L1 instead of 60 KB for the edge and prologue loads), so each kernel keeps its own split.
+static const bool g_same_carveout = getenv("TEALEAF_B200_CARVEOUT") && atoi(getenv("TEALEAF_B200_CARVEOUT")) == 1;
 template <typename P>
 static int tl_prepare_smem(tl_ctx *c, void (*kern)(const P), int smem, unsigned long long *device_mask) {
   const unsigned long long bit = 1ull << (c->device & 63);
   if (!(*device_mask & bit)) {
-    CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (smem > 0) CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // every kernel of the iteration loops asks for the SAME L1 / shared-memory split (all shared): two consecutive
+    // kernels with different carve-outs make the SMs reconfigure between them, which lengthens the launch gap
+    if (g_same_carveout) CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     *device_mask |= bit;
   }
   return TL_OK;
@@ -516,6 +525,10 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "ppcg_pair") c->ppcg_pair = value != 0.0;
   else if (n == "pair_tiled") c->pair_tiled = value != 0.0;
   else if (n == "pair_rows") c->pair_rows = std::max(2, (int)value);
+  else if (n == "pair_stages") {
+    if ((int)value != 4 && (int)value != 5) return tl_fail(c, TL_ERR_ARG, "pair_stages must be 4 or 5");
+    c->pair_stages = (int)value;
+  }
   else if (n == "b_ring") {
     const int d = (int)value;
     if (d != 0 && d != 6 && d != 8) return tl_fail(c, TL_ERR_ARG, "b_ring must be 0, 6 or 8");
@@ -581,6 +594,7 @@ extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
   else if (n == "ppcg_pair") v = c->ppcg_pair;
   else if (n == "pair_tiled") v = c->pair_tiled;
   else if (n == "pair_rows") v = c->pair_rows;
+  else if (n == "pair_stages") v = c->pair_stages;
   else if (n == "b_ring") v = c->b_ring;
   else if (n == "ppcg_halo_depth") v = c->ppcg_depth_k;
   else if (n == "l2_persist_mb") v = c->l2_persist_mb;
@@ -1341,7 +1355,12 @@ static int launch_b_ring(tl_ctx *c, const CgBParams &P) {
 static int launch_cg_b(tl_ctx *c) {
   const CgBParams P = cg_b_params(c);
   switch (c->b_ring) {
-    case 0: CU(c, tl_launch(c, k_cg_fused_r, c->pw_grid, TL_FUSED_THREADS, 0, P)); break;
+    case 0: {
+      static unsigned long long prepared = 0;
+      TRY(tl_prepare_smem(c, k_cg_fused_r, 0, &prepared));
+      CU(c, tl_launch(c, k_cg_fused_r, c->pw_grid, TL_FUSED_THREADS, 0, P));
+      break;
+    }
     case 6: TRY((launch_b_ring<6, 4>(c, P))); break;
     case 8: TRY((launch_b_ring<8, 3>(c, P))); break;
     default: return tl_fail(c, TL_ERR_STATE, "internal: b_ring %d", c->b_ring);
@@ -1617,10 +1636,12 @@ static int enqueue_cheby_pair(tl_ctx *c) {
   if (c->nranks > 1) {
     P.push_ua = push8_for(c, TL_U); P.push_ub = push8_for(c, B_U1);
     P.push_p0 = push8_for(c, TL_P); P.push_p1 = push8_for(c, B_P1);
-    TRY((launch_cheby_pair_ring<4, 2, true>(c, P)));
+    if (c->pair_stages == 5) TRY((launch_cheby_pair_ring<5, 2, true>(c, P)));
+    else TRY((launch_cheby_pair_ring<4, 2, true>(c, P)));
   } else {
     memset(&P.push_ua, 0, 4 * sizeof(Push8));
-    TRY((launch_cheby_pair_ring<4, 2, false>(c, P)));
+    if (c->pair_stages == 5) TRY((launch_cheby_pair_ring<5, 2, false>(c, P)));
+    else TRY((launch_cheby_pair_ring<4, 2, false>(c, P)));
   }
   CHECK_LAUNCH(c);
   c->launches++;
@@ -1864,6 +1885,10 @@ static PpcgPairParams ppcg_pair_params(tl_ctx *c, int k, int npairs) {
 }
 static int launch_ppcg_pair(tl_ctx *c, int k, int npairs) {
   const PpcgPairParams P = ppcg_pair_params(c, k, npairs);
+  if (c->pair_stages == 5) {
+    if (c->nranks > 1) return launch_ppcg_pair_ring<5, 2, true>(c, P);
+    return launch_ppcg_pair_ring<5, 2, false>(c, P);
+  }
   if (c->nranks > 1) return launch_ppcg_pair_ring<4, 2, true>(c, P);
   return launch_ppcg_pair_ring<4, 2, false>(c, P);
 }
@@ -1886,6 +1911,10 @@ static int launch_ppcg_trailing(tl_ctx *c, int npairs) {
   return TL_OK;
 }
 
+static int prepare_ur_sd(tl_ctx *c) {
+  static unsigned long long prepared = 0;
+  return tl_prepare_smem(c, k_ppcg_ur_sd, 0, &prepared);
+}
 static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k, bool pairs) {
   const bool legacy = legacy_comm(c);
   if (pairs) {
@@ -1897,6 +1926,7 @@ static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k, bool pair
       U.deep = 1; U.r_out = c->buf[rin0]; U.d_sd = 2; U.d_r = 1;
       U.push_sd8 = push8_for(c, TL_SD); U.push_r8 = push8_for(c, rin0);
     } else if (rin0 != TL_R) { U.deep = 1; U.r_out = c->buf[rin0]; U.d_sd = 1; U.d_r = 0; }
+    TRY(prepare_ur_sd(c));
     CU(c, tl_launch(c, k_ppcg_ur_sd, c->pw_grid, TL_FUSED_THREADS, 0, U));
     for (int k = 0; k < npairs; k++) TRY(launch_ppcg_pair(c, k, npairs));
     if (inner_steps & 1) TRY(launch_ppcg_trailing(c, npairs));
@@ -1907,6 +1937,7 @@ static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k, bool pair
   if (depth_k > 1) {
     // matrix-powers groups: one tile exchange per depth_k inner steps (PpcgDkParams)
     TRY(launch_cg_a<false>(c));
+    TRY(prepare_ur_sd(c));
     CU(c, tl_launch(c, k_ppcg_ur_sd, c->pw_grid, TL_FUSED_THREADS, 0, ppcg_ur_params_dk(c, inner_steps, depth_k)));
     for (int pp = 0; pp < inner_steps; pp++) TRY(launch_ppcg_dk(c));
     c->launches += 2 + inner_steps;
@@ -1919,6 +1950,7 @@ static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k, bool pair
   }
   TRY(launch_cg_a<false>(c));
   if (legacy) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
+  TRY(prepare_ur_sd(c));
   CU(c, tl_launch(c, k_ppcg_ur_sd, c->pw_grid, TL_FUSED_THREADS, 0, ppcg_ur_params(c)));
   for (int pp = 0; pp < inner_steps; pp++) {
     if (legacy) {

@@ -230,6 +230,11 @@ __device__ __forceinline__ unsigned long long tl_ld_relaxed_sys(const unsigned l
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long tl_ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned long long tl_globaltimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -291,8 +296,9 @@ __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState
     }
     sm[1 + threadIdx.x] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
     // acquire side, by the threads that observed the slots: later reads (the next kernel's halo loads) see the
-    // neighbours' pushes that were ordered before those slots
-    __threadfence_system();
+    // neighbours' pushes that were ordered before those slots.  An acquire LOAD of the slot just observed, not a
+    // fence.sys: the fence would also wait for this thread's own packet stores to be acknowledged across NVLink.
+    (void)tl_ld_acquire_sys(&src->hi);
   }
   __syncthreads();
   double total = 0.0;

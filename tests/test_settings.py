@@ -138,3 +138,27 @@ def test_debugrecord_dump_follows_the_reference_format(tmp_path):
     assert len(dens) == 5 + 4 and all(len(row.split(" ")) == 6 + 4 for row in dens)
     assert {v for row in dens for v in row.split(" ")} == {"100.0", "0.1"}
 
+
+
+def test_literal_nudge_switch_reproduces_the_unpatched_reference():
+    """`readstate` runs inside the line loop, before dx, dy are recomputed (src/settings.jl:98-100 vs :132-133), so the
+    literal reference always nudges the state rectangles by the DEFAULT dx/100 = 10/100 = 0.1.  The
+    mirror's default is the intended two-pass nudge; literal_nudge=True reproduces the unpatched behaviour."""
+    import tealeaf_jl_b200 as tl
+    from tealeaf_jl_b200.decks import CLASSIC_DECK
+    text = CLASSIC_DECK.format(nx=200, ny=100, steps=1, solver="cg")
+    s = tl.parse_settings_text(text)
+    lit = tl.parse_settings_text(text, literal_nudge=True)
+    assert abs(s.dx - 0.05) < 1e-15 and abs(s.dy - 0.1) < 1e-15
+    st, sl = s.states[1], lit.states[1]             # state 2: xmin=0.0 xmax=1.0 ymin=1.0 ymax=2.0
+    assert abs(st.xmin - 0.0005) < 1e-15 and abs(st.xmax - 0.9995) < 1e-12 and abs(st.ymin - 1.001) < 1e-12
+    assert abs(sl.xmin - 0.1) < 1e-15 and abs(sl.xmax - 0.9) < 1e-15 and abs(sl.ymin - 1.1) < 1e-15 and abs(sl.ymax - 1.9) < 1e-15
+    lit.xcells = 400                                 # -x / -y overrides recompute the spacing, not the literal nudge
+    lit.recompute_spacing()
+    assert abs(lit.states[1].xmin - 0.1) < 1e-15
+    # the painted regions differ: what the Julia-hosted path paints without the two-pass fix
+    from tealeaf_jl_b200.chunk import HostGeometry, paint_states
+    lit = tl.parse_settings_text(text, literal_nudge=True)
+    d1, _, _ = paint_states(s, HostGeometry(s))
+    d2, _, _ = paint_states(lit, HostGeometry(lit))
+    assert (d1 != d2).sum() > 0
