@@ -138,6 +138,7 @@ struct tl_ctx {
   int cg_persist = 0;       // 1: the CG loop of a single tile runs as ONE persistent cooperative kernel (tl_kernels_persist.cuh)
   PersistSync *psync = nullptr;
   int comm_fused = 1;       // 1: halo pushes + mailbox allreduce inside the kernels; 0: halo-pull kernels + NCCL
+  int xchg_deferred = 0;    // 1: split exchange -- kernels post their packets in the tail, the NEXT kernel collects them at its entry
   CommDev *d_comm = nullptr;   // device copy of the mailbox table (in the slab)
   MailSlot *mail = nullptr;
 #ifdef TL_WITH_NCCL
@@ -368,6 +369,10 @@ extern "C" const char *tl_last_error(const tl_ctx *c) { return c ? c->err.c_str(
 extern "C" int tl_set_option(tl_ctx *c, const char *name, double value);
 extern "C" void tl_destroy(tl_ctx *c);
 
+__global__ void k_zero_words(unsigned long long *p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0ull;
+}
+
 extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_depth, int max_iters, int device,
                               int rank, int px, int py) {
   if (!out) return TL_ERR_ARG;
@@ -443,6 +448,15 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
     return TL_ERR_CUDA;
   }
   compute_tiling(c);
+  // The control block (solve state, partials, mailboxes, mailbox table) is written once more by ordinary stores of a
+  // kernel: cudaMemset may leave its lines in the memory system's cleared-line state, and the first 8-byte packet another
+  // tile's kernel stored into such a line was occasionally never seen by the polling tile (tiles sharing one GPU,
+  // profiles/r02f_multi_stress_*.log).
+  if (!getenv("TL_NO_TOUCH")) {
+    const size_t words = (bytes - off_state) / sizeof(unsigned long long);
+    k_zero_words<<<64, 256, 0, c->stream>>>((unsigned long long *)(c->slab + off_state), words);
+    cudaStreamSynchronize(c->stream);
+  }
   cudaDeviceSynchronize();
   *out = c;
   // default options for every context of the process: TEALEAF_B200_OPTS="name=value,name=value"
@@ -513,6 +527,18 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "hint_stream") c->hint_stream = std::min(std::max(0, (int)value), 2);
   else if (n == "b_reverse") c->b_reverse = value != 0.0;
   else if (n == "comm_fused") c->comm_fused = value != 0.0;
+  else if (n == "xchg_deferred") {
+    c->xchg_deferred = value != 0.0;
+    if (c->comm_ready && c->nranks > 1) {   // the kernels read the switch from the device copy of the mailbox table
+      cudaSetDevice(c->device);
+      cudaStreamSynchronize(c->stream);
+      const int flag[2] = {c->xchg_deferred, 0};
+      memcpy(c->h_scal, flag, sizeof flag);
+      if (cudaMemcpyAsync(&c->d_comm->deferred, c->h_scal, sizeof flag, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+          cudaStreamSynchronize(c->stream) != cudaSuccess)
+        return tl_fail(c, TL_ERR_CUDA, "xchg_deferred: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
   else if (n == "use_pdl") c->use_pdl = value != 0.0;   // programmatic dependent launch, released before the kernel tails (tl_pdl_trigger)
   else if (n == "cg_persist") c->cg_persist = value != 0.0;
   else if (n == "a_tma") {   // 0 off; 1 / 4: TMA ring of 4 row slots; 3: of 3 row slots (two CTAs per SM either way)
@@ -586,6 +612,7 @@ extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
   else if (n == "hint_stream") v = c->hint_stream;
   else if (n == "b_reverse") v = c->b_reverse;
   else if (n == "comm_fused") v = c->comm_fused;
+  else if (n == "xchg_deferred") v = c->xchg_deferred;
   else if (n == "use_pdl") v = c->use_pdl;
   else if (n == "cg_persist") v = c->cg_persist;
   else if (n == "a_tma") v = c->a_tma;
@@ -694,7 +721,7 @@ extern "C" int tl_comm_connect(tl_ctx *c, const void *all_blobs, const void *id1
   // only touched on the eight neighbours
   CommDev hd;
   memset(&hd, 0, sizeof hd);
-  hd.nranks = c->nranks; hd.rank = c->rank;
+  hd.nranks = c->nranks; hd.rank = c->rank; hd.deferred = c->xchg_deferred;
   const long long me = (long long)getpid();
   for (int r = 0; r < c->nranks; r++) {
     if (blobs[r].rank != r) return tl_fail(c, TL_ERR_ARG, "tl_comm_connect: blobs are not in rank order");
@@ -754,6 +781,8 @@ extern "C" int tl_comm_connect(tl_ctx *c, const void *all_blobs, const void *id1
 // included) is ordered before the mailbox stores by the fence.sys + bar.sync at the start.
 __global__ void k_tile_allreduce(const CommDev *cd, SolveState *st, const double *src, double *dst, int n) {
   __shared__ double sm[32];
+  (void)tl_entry_scalars(cd, st);   // split exchange: collect what a loop kernel posted before exchanging again
+  __syncthreads();
   if (st->comm_error) return;
   if (threadIdx.x == blockDim.x - 1) __threadfence_system();
   for (int q = 0; q < n; q++) {
@@ -761,6 +790,18 @@ __global__ void k_tile_allreduce(const CommDev *cd, SolveState *st, const double
     const double t = tl_tile_exchange(cd, st, v, sm);
     if (threadIdx.x == 0) dst[q] = t;
   }
+}
+
+// Split exchange: publishes the total of the exchange the last loop kernel posted (nobody collected it yet) into the
+// SolveState.  Enqueued wherever the host, or a kernel that reads the SolveState directly, comes next.
+__global__ void k_xchg_finalize(const CommDev *cd, SolveState *st) { (void)tl_entry_scalars(cd, st); }
+static bool xchg_deferred(const tl_ctx *c) { return c->nranks > 1 && c->comm_fused && c->xchg_deferred; }
+static int xchg_finalize(tl_ctx *c) {
+  if (!xchg_deferred(c)) return TL_OK;
+  k_xchg_finalize<<<1, 32, 0, c->stream>>>(c->d_comm, c->st);
+  c->launches++;
+  CHECK_LAUNCH(c);
+  return TL_OK;
 }
 
 // sum over tiles of n doubles living in device memory (stream ordered); out of place when
@@ -965,13 +1006,27 @@ static int check_comm(tl_ctx *c, const char *where) {
   SolveState *h = &c->h_st[0];
   CU(c, cudaMemcpyAsync(h, c->st, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  if (h->comm_error)
-    return tl_fail(c, TL_ERR_COMM, "%s: tile exchange timed out: tile %d did not hear from tile %d in exchange %llu", where, c->rank,
-                   h->comm_error - 1, h->xseq);
+  if (h->comm_error) {
+    // where this tile's packets of its last blocking exchange went, against where the table says they belong
+    std::string tgt;
+    for (int r = 0; r < c->nranks; r++) {
+      const MailSlot *base = (r == c->rank) ? c->mail : (const MailSlot *)((char *)c->rank_slab[r] + c->rank_blob[r].mail_offset);
+      const long long off = (long long)(h->dbg_dst[r] - (unsigned long long)(uintptr_t)base);
+      char b[64];
+      snprintf(b, sizeof b, "%s%d:%s%lld", r ? " " : "", r, (off >= 0 && off < (long long)(2 * TL_MAX_RANKS * sizeof(MailSlot))) ? "+" : "STRAY", off);
+      tgt += b;
+    }
+    const int who = h->comm_error - 1;
+    return tl_fail(c, TL_ERR_COMM, "%s: tile exchange timed out: tile %d did not hear from tile %d in exchange %llu (slot held exchange numbers "
+                   "%u/%u; this tile's packet offsets in the destination mailboxes: %s)", where, c->rank, who, h->xseq,
+                   (unsigned)(h->dbg_seen[who & 15] >> 32), (unsigned)h->dbg_seen[who & 15], tgt.c_str());
+  }
   return TL_OK;
 }
 
+static int xchg_finalize(tl_ctx *c);
 static int read_scalars(tl_ctx *c, const double *dev, int n, double *out) {
+  TRY(xchg_finalize(c));   // split exchange: a loop kernel may have posted the value that is read here
   CU(c, cudaMemcpyAsync(c->h_scal, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < n; i++) out[i] = c->h_scal[i];
@@ -1395,6 +1450,7 @@ static int build_graph(tl_ctx *c, cudaGraphExec_t *exec, int reps, F enqueue_one
   int rc = TL_OK;
   const long long saved = c->launches;
   for (int i = 0; i < reps && rc == TL_OK; i++) rc = enqueue_one();
+  if (rc == TL_OK) rc = xchg_finalize(c);   // the host reads the state after every chunk
   c->launches = saved;
   cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -1419,9 +1475,10 @@ static int run_chunks(tl_ctx *c, cudaGraphExec_t *exec, int *exec_iters, int chu
   for (;; k++) {
     if (c->use_graph) {
       CU(c, cudaGraphLaunch(*exec, c->stream));
-      c->launches += launches_per_iter * chunk_iters;
+      c->launches += launches_per_iter * chunk_iters + (xchg_deferred(c) ? 1 : 0);
     } else {
       for (int i = 0; i < chunk_iters; i++) TRY(enqueue_one());
+      TRY(xchg_finalize(c));
     }
     CU(c, cudaMemcpyAsync(&c->h_st[k & 1], c->st, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaEventRecord(c->ev[k & 1], c->stream));
@@ -2228,6 +2285,7 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
   CU(c, cudaEventRecord(c->ev_start, c->stream));
   for (int i = 0; i < reps; i++) TRY(launch());
   CU(c, cudaEventRecord(c->ev_stop, c->stream));
+  TRY(xchg_finalize(c));
   CU(c, cudaEventSynchronize(c->ev_stop));
   CHECK_LAUNCH(c);
   float ms = 0.f;

@@ -46,6 +46,7 @@ struct StopCfg {
 
 // Device-resident scalars of a solve.  Written only by the last block of a kernel (all other
 // blocks of that kernel have finished by then), read by every block of later kernels.
+#define TL_MAX_RANKS 16
 struct SolveState {
   StopCfg cfg;
   int iter;             // completed CG-type iterations (CG.jl:18 `tt`, PPCG outer included)
@@ -78,6 +79,14 @@ struct SolveState {
   double barrier_zero, barrier_out;
   // micro-profile of the kernel boundaries (option "prof"; tl_get_option "prof_*"): globaltimer stamps taken by
   // block 0 at kernel entry and by the LAST block around the grid sum, the fence.sys and the tile exchange
+  // split tile exchange (CommDev::deferred): the exchange the previous kernel POSTED in its tail and that nobody has
+  // collected yet -- number, which scalar it carries (TL_T_*), and the number of the last exchange block 0 of a later
+  // kernel has published into red_pw / red_rr / red_norm
+  unsigned long long pend_seq, coll_seq;
+  int pend_target, pad3;
+  // diagnostics of the last blocking exchange: where thread q sent its packet and what the slot it waited on held
+  // when it gave up (reported with a time-out: tl_api.cu check_comm)
+  unsigned long long dbg_dst[TL_MAX_RANKS], dbg_seen[TL_MAX_RANKS];
   int prof, pad2;
   unsigned long long prof_start, prof_prev_end;
   unsigned long long prof_acc[6];   // ns: [0] entry -> last block in the tail, [1] ticket + partial sums, [2] tile exchange,
@@ -85,7 +94,6 @@ struct SolveState {
 };
 
 // ---- multi-GPU: peer-mapped mailboxes and halo push targets --------------------------------
-#define TL_MAX_RANKS 16
 #define TL_XCHG_TIMEOUT_NS 10000000000ull
 // One slot per (parity, sender), "LL" packets: each 8-byte word carries 32 bits of the double and
 // the low 32 bits of the exchange number, so one (atomic) 8-byte store publishes data and flag
@@ -94,7 +102,14 @@ struct MailSlot { unsigned long long lo, hi; };
 struct CommDev {
   int nranks, rank;
   MailSlot *mail[TL_MAX_RANKS];   // mail[r] = rank r's mailbox (2 x TL_MAX_RANKS slots), CUDA-IPC mapped
+  int deferred, pad;              // 1: kernels post their packets in the tail and the NEXT kernel collects them at its entry
 };
+// which scalar of the SolveState an exchange carries
+#define TL_T_NONE 0
+#define TL_T_PW 1
+#define TL_T_RR 2
+#define TL_T_NORM 3
+struct TlScal { double pw, rr, norm; };
 // Where the edge cells of ONE buffer go: the same buffer of the neighbour tile on each
 // tile-internal side (0 left, 1 right, 2 bottom, 3 top); f0 = interior origin, null on physical sides.
 struct PushSide { double *f0; int pitch, nx, ny; };
@@ -276,6 +291,7 @@ __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState
     MailSlot *dst = (MailSlot *)tl_ld_relaxed_sys((const unsigned long long *)&cd->mail[threadIdx.x]) + par * TL_MAX_RANKS + my_rank;
     tl_st_relaxed_sys(&dst->lo, w_lo);
     tl_st_relaxed_sys(&dst->hi, w_hi);
+    st->dbg_dst[threadIdx.x] = (unsigned long long)(uintptr_t)dst;
     const MailSlot *src = (const MailSlot *)tl_ld_relaxed_sys((const unsigned long long *)&cd->mail[my_rank]) + par * TL_MAX_RANKS + threadIdx.x;
     unsigned long long lo, hi;
     unsigned spins = 0;
@@ -287,7 +303,11 @@ __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState
       if ((++spins & 1023u) == 0u) {   // a neighbour that never arrives must not hang the GPU
         const unsigned long long t = tl_globaltimer();
         if (t0 == 0) t0 = t;
-        else if (t - t0 > TL_XCHG_TIMEOUT_NS) { st->comm_error = 1 + (int)threadIdx.x; break; }   // 1 + the rank not heard from
+        else if (t - t0 > TL_XCHG_TIMEOUT_NS) {   // 1 + the rank not heard from
+          st->comm_error = 1 + (int)threadIdx.x;
+          st->dbg_seen[threadIdx.x] = (lo & 0xffffffff00000000ull) | (hi >> 32);   // exchange numbers found in the slot
+          break;
+        }
         // the packet is idempotent (same exchange number, same value): post it again while waiting
         dst = (MailSlot *)tl_ld_relaxed_sys((const unsigned long long *)&cd->mail[threadIdx.x]) + par * TL_MAX_RANKS + my_rank;
         tl_st_relaxed_sys(&dst->lo, w_lo);
@@ -307,11 +327,98 @@ __device__ __forceinline__ double tl_tile_exchange(const CommDev *cd, SolveState
   return total;
 }
 
+// ---- split exchange: post in the tail, collect at the next kernel's entry ----------------------------------------
+// The blocking exchange above makes the last block of a kernel wait for the slowest tile while every SM idles, and only
+// then can the next kernel be launched.  Split form: the last block POSTS its packets and the kernel ends; every block
+// of the NEXT kernel of the stream waits for the n packets at its entry and adds them in rank order (same bits on every
+// tile and in every block), so the wait for the slowest tile overlaps the launch gap.  Block 0 also publishes the total
+// into the SolveState for the host.  The guarantees are the blocking exchange's: a tile starts kernel k+1 only after
+// every tile has finished kernel k (halo pushes complete, ping-pong buffers free); a slot of parity p is rewritten by
+// exchange n+2 only after the receiver's kernel that collected exchange n has finished.
+__device__ __forceinline__ bool tl_is_deferred(const CommDev *cd) { return cd != nullptr && cd->deferred != 0; }
+
+// last block, all threads; v valid in thread 0.  Preceded by the fence.sys of the tail.
+__device__ __forceinline__ void tl_tile_post(const CommDev *cd, SolveState *st, double v, int target, double *sm) {
+  __shared__ unsigned long long s_pseq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sm[0] = v;
+    s_pseq = st->xseq + 1;
+    st->xseq = s_pseq;
+    st->pend_target = target;
+    st->pend_seq = s_pseq;
+  }
+  __syncthreads();
+  const int n = (int)tl_ld_relaxed_sys((const unsigned long long *)&cd->nranks);
+  const int my_rank = (int)(tl_ld_relaxed_sys((const unsigned long long *)&cd->nranks) >> 32);
+  const unsigned seq = (unsigned)s_pseq;
+  if ((int)threadIdx.x < n) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(sm[0]);
+    MailSlot *dst = (MailSlot *)tl_ld_relaxed_sys((const unsigned long long *)&cd->mail[threadIdx.x]) + (seq & 1u) * TL_MAX_RANKS + my_rank;
+    tl_st_relaxed_sys(&dst->lo, ((unsigned long long)seq << 32) | (bits & 0xffffffffull));
+    tl_st_relaxed_sys(&dst->hi, ((unsigned long long)seq << 32) | (bits >> 32));
+  }
+}
+
+// Kernel entry, every thread: the scalars this kernel works with -- the SolveState's, with the total of a posted and not
+// yet collected exchange patched in.  Returns with comm_error set if a tile never posted.
+__device__ __forceinline__ TlScal tl_entry_scalars(const CommDev *cd, SolveState *st) {
+  TlScal S;
+  if (!tl_is_deferred(cd)) {
+    S.pw = st->red_pw; S.rr = st->red_rr; S.norm = st->red_norm;
+    return S;
+  }
+  const unsigned long long pseq = *(volatile unsigned long long *)&st->pend_seq;
+  const unsigned long long cseq = *(volatile unsigned long long *)&st->coll_seq;
+  __threadfence();   // block 0 publishes the totals, fences, then sets coll_seq: read in the opposite order
+  S.pw = *(volatile double *)&st->red_pw; S.rr = *(volatile double *)&st->red_rr; S.norm = *(volatile double *)&st->red_norm;
+  if (pseq == cseq) return S;     // nothing pending, or block 0 of this kernel has published it already
+  const bool prof = st->prof != 0 && blockIdx.x == 0 && threadIdx.x == 0;
+  const unsigned long long tp = prof ? tl_globaltimer() : 0;
+  const int n = (int)tl_ld_relaxed_sys((const unsigned long long *)&cd->nranks);
+  const int my_rank = (int)(tl_ld_relaxed_sys((const unsigned long long *)&cd->nranks) >> 32);
+  const unsigned seq = (unsigned)pseq;
+  const MailSlot *box = (const MailSlot *)tl_ld_relaxed_sys((const unsigned long long *)&cd->mail[my_rank]) + (seq & 1u) * TL_MAX_RANKS;
+  double total = 0.0;
+  unsigned long long t0 = 0;
+  for (int r = 0; r < n; r++) {          // warp-uniform addresses: one L2 transaction per warp and load
+    unsigned long long lo, hi;
+    unsigned spins = 0;
+    for (;;) {
+      lo = tl_ld_relaxed_sys(&box[r].lo);
+      hi = tl_ld_relaxed_sys(&box[r].hi);
+      if ((unsigned)(lo >> 32) == seq && (unsigned)(hi >> 32) == seq) break;
+      if ((++spins & 1023u) == 0u) {
+        const unsigned long long t = tl_globaltimer();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > TL_XCHG_TIMEOUT_NS) { st->comm_error = 1 + r; return S; }
+      }
+    }
+    total += __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+  }
+  (void)tl_ld_acquire_sys(&box[0].hi);   // acquire: the halo loads below see what the tiles pushed before posting
+  const int target = st->pend_target;
+  if (target == TL_T_PW) S.pw = total;
+  else if (target == TL_T_RR) S.rr = total;
+  else if (target == TL_T_NORM) S.norm = total;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {     // for the host and for kernels that read the SolveState directly
+    if (target == TL_T_PW) st->red_pw = total;
+    else if (target == TL_T_RR) st->red_rr = total;
+    else if (target == TL_T_NORM) st->red_norm = total;
+    __threadfence();
+    *(volatile unsigned long long *)&st->coll_seq = pseq;
+    if (prof) st->prof_acc[2] += tl_globaltimer() - tp;
+  }
+  return S;
+}
+
 // Common end of a hot-loop kernel: grid-wide sum of acc[0] (do_sum) or just the last-block
 // ticket, then -- when tiles exchange (cd != null) -- the all-tiles sum / barrier.  Returns true
 // in thread 0 of the last block, with acc[0] = the (global) total.
+// `target`: which SolveState scalar the sum is (TL_T_*).  With the split exchange (tl_is_deferred) acc[0] stays this
+// tile's LOCAL sum: the caller must not publish it as the all-tiles value -- the next kernel's entry does.
 __device__ __forceinline__ bool tl_kernel_tail(double (&acc)[1], bool do_sum, SolveState *st, double *partials,
-                                               const CommDev *cd, double *sm) {
+                                               const CommDev *cd, double *sm, int target = TL_T_NONE) {
   const bool prof = st->prof != 0;
   unsigned long long t_in = 0;
   if (prof && threadIdx.x == 0) t_in = tl_globaltimer();
@@ -339,7 +446,8 @@ __device__ __forceinline__ bool tl_kernel_tail(double (&acc)[1], bool do_sum, So
   if (!last) return false;
   unsigned long long t_sum = 0;
   if (prof && threadIdx.x == 0) t_sum = tl_globaltimer();
-  if (cd) acc[0] = tl_tile_exchange(cd, st, acc[0], sm);
+  if (tl_is_deferred(cd)) tl_tile_post(cd, st, acc[0], do_sum ? target : TL_T_NONE, sm);
+  else if (cd) acc[0] = tl_tile_exchange(cd, st, acc[0], sm);
   if (prof && threadIdx.x == 0) {
     const unsigned long long t_end = tl_globaltimer();
     const unsigned long long t_start = *(volatile unsigned long long *)&st->prof_start;

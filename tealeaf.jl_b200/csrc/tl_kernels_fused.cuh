@@ -202,17 +202,18 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBPar
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const TlScal sc = tl_entry_scalars(P.cd, st);
   const int it = st->iter;
-  const double rr_cur = st->red_rr;
+  const double rr_cur = sc.rr;
   if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
-  const double pw = st->red_pw;
+  const double pw = sc.pw;
   const double alpha = rr_cur / pw;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_pw[it + 1] = pw;
   double acc[1] = {0.0};
   tl_cg_b_item<false>(P, alpha, blockIdx.x, acc[0]);
-  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm, TL_T_RR)) {
     st->red_rr_local = acc[0];
-    if (P.single || P.cd != nullptr) st->red_rr = acc[0];
+    if ((P.single || P.cd != nullptr) && !tl_is_deferred(P.cd)) st->red_rr = acc[0];
     st->iter = it + 1;
   }
 }
@@ -293,12 +294,14 @@ __host__ __device__ inline bool tl_cheby_is_norm_iter(int chebyiters, int tt0, i
 // Stop rule of the Chebyshev loop after `step` kernels (init included), evaluated at the entry
 // of every kernel and by the host: converged on the last norm (Cheby.jl:57, summed over the
 // tiles) or out of iterations.
-__host__ __device__ inline bool tl_cheby_should_stop(const SolveState &s) {
+// `norm`: the latest all-tiles norm (s.red_norm, or the total a kernel collected at its entry: split exchange)
+__host__ __device__ inline bool tl_cheby_should_stop_n(const SolveState &s, double norm) {
   const int done_iters = s.cheby_step - 1;   // completed main steps
-  if (done_iters >= 1 && tl_cheby_is_norm_iter(done_iters, s.cheby_tt0, s.cheby_est) && fabs(s.red_norm) < s.eps_cheby)
+  if (done_iters >= 1 && tl_cheby_is_norm_iter(done_iters, s.cheby_tt0, s.cheby_est) && fabs(norm) < s.eps_cheby)
     return true;
   return s.cheby_tt0 + s.cheby_step - 1 > s.cheby_max_tt;
 }
+__host__ __device__ inline bool tl_cheby_should_stop(const SolveState &s) { return tl_cheby_should_stop_n(s, s.red_norm); }
 
 // ------------------------------------------------------------------------------------------
 // PPCG.  Outer iteration = k_cg_fused_w_ring<false> (w = A p, pw)  ->  k_ppcg_ur_sd  ->
@@ -327,10 +330,11 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_ppcg_ur_sd(const PpcgUr
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const TlScal sc = tl_entry_scalars(P.cd, st);
   const int it = st->iter;
-  const double rr_cur = st->red_rr;
+  const double rr_cur = sc.rr;
   if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
-  const double pw = st->red_pw, alpha = rr_cur / pw, theta = st->theta;
+  const double pw = sc.pw, alpha = rr_cur / pw, theta = st->theta;
   if (blockIdx.x == 0 && threadIdx.x == 0) { P.hist_pw[it + 1] = pw; st->inner_pp = 0; }
   // kernel A of this iteration wrote p into the (it&1 ? p0 : p1) buffer
   const double *__restrict__ p = (it & 1) ? P.p0 : P.p1;

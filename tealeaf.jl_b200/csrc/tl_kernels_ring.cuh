@@ -184,8 +184,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const TlScal sc = tl_entry_scalars(P.cd, st);
   const int it = st->iter;
-  const double rr_cur = st->red_rr;
+  const double rr_cur = sc.rr;
   if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
   CgAIter I;
   I.it = it;
@@ -199,9 +200,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
   if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_rr[it] = rr_cur;
   double acc[1] = {0.0};
   tl_cg_a_item<UPDATE_U, S, false>(P, I, blockIdx.x, ring_raw, acc[0]);
-  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm, TL_T_PW)) {
     st->red_pw_local = acc[0];
-    if (P.single || P.cd != nullptr) st->red_pw = acc[0];
+    if ((P.single || P.cd != nullptr) && !tl_is_deferred(P.cd)) st->red_pw = acc[0];
   }
 }
 
@@ -270,17 +271,18 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_r_ring(cons
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const TlScal sc = tl_entry_scalars(P.cd, st);
   const int it = st->iter;
-  const double rr_cur = st->red_rr;
+  const double rr_cur = sc.rr;
   if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
-  const double pw = st->red_pw;
+  const double pw = sc.pw;
   const double alpha = rr_cur / pw;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_pw[it + 1] = pw;
   double acc[1] = {0.0};
   tl_cg_b_item_ring<D, false>(P, alpha, blockIdx.x, ring_raw, acc[0]);
-  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm, TL_T_RR)) {
     st->red_rr_local = acc[0];
-    if (P.single || P.cd != nullptr) st->red_rr = acc[0];
+    if ((P.single || P.cd != nullptr) && !tl_is_deferred(P.cd)) st->red_rr = acc[0];
     st->iter = it + 1;
   }
 }
@@ -369,6 +371,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const TlScal sc = tl_entry_scalars(P.cd, st);
   const int step = st->cheby_step;
   double alpha = 0.0, beta = 0.0;
   bool calc_norm, store_wr;
@@ -376,8 +379,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
   if (FIRST) {
     calc_norm = true;
     store_wr = true;
+    if (st->comm_error) return;
   } else {
-    if (st->comm_error || tl_cheby_should_stop(*st)) return;
+    if (st->comm_error || tl_cheby_should_stop_n(*st, sc.norm)) return;
     const int chebyiters = step;
     const int tt = st->cheby_tt0 + chebyiters - 1;
     alpha = P.alphas[chebyiters];
@@ -454,10 +458,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_fused_ring(con
     tl_cp_wait<0>();
   }
   // no reduction on most iterations: only the ticket (and, tiled, the completion barrier)
-  if (tl_kernel_tail(acc, calc_norm, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, calc_norm, st, P.partials, P.cd, sm, TL_T_NORM)) {
     if (calc_norm) {
       st->red_norm_local = acc[0];
-      if (P.single || tiled) st->red_norm = acc[0];
+      if ((P.single || tiled) && !tl_is_deferred(P.cd)) st->red_norm = acc[0];
     }
     st->cheby_step = step + 1;
   }
@@ -501,8 +505,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_ring(cons
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const CommDev *xcd = TILED ? P.cd : nullptr;
+  const TlScal sc = tl_entry_scalars(xcd, st);
   const int step = st->cheby_step;
-  if (st->comm_error || tl_cheby_should_stop(*st)) return;
+  if (st->comm_error || tl_cheby_should_stop_n(*st, sc.norm)) return;
   const int ttA = st->cheby_tt0 + step - 1;
   if (ttA + 1 > st->cheby_max_tt) return;                                            // step B not permitted
   if (tl_cheby_is_norm_iter(step, st->cheby_tt0, st->cheby_est)) return;            // never (see above): guard
@@ -612,10 +618,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cheby_pair_ring(cons
     }
   }
   // tiles: all-tiles norm / completion barrier of the halo pushes
-  if (tl_kernel_tail(acc, calc_norm, st, P.partials, TILED ? P.cd : nullptr, sm)) {
+  if (tl_kernel_tail(acc, calc_norm, st, P.partials, xcd, sm, TL_T_NORM)) {
     if (calc_norm) {
       st->red_norm_local = acc[0];
-      st->red_norm = acc[0];
+      if (!tl_is_deferred(xcd)) st->red_norm = acc[0];
     }
     st->cheby_step = step + 2;
     st->cheby_pairs = pairs + 1;
@@ -634,8 +640,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_pair_ring(const
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const CommDev *xcd = TILED ? P.cd : nullptr;
+  const TlScal sc = tl_entry_scalars(xcd, st);
   const int it = st->iter;
-  if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
+  if (st->comm_error || tl_should_stop(it, sc.rr, st->cfg)) return;
   const int pp = st->inner_pp;
   const bool last = (pp + 2 == st->inner_steps);
   const double alphaA = P.alphas[pp], betaA = P.betas[pp];
@@ -732,10 +740,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_pair_ring(const
       tl_cp_wait<0>();
     }
   }
-  if (tl_kernel_tail(acc, last, st, P.partials, TILED ? P.cd : nullptr, sm)) {
+  if (tl_kernel_tail(acc, last, st, P.partials, xcd, sm, TL_T_RR)) {
     if (last) {
       st->red_rr_local = acc[0];      // PPCG.jl:88
-      st->red_rr = acc[0];
+      if (!tl_is_deferred(xcd)) st->red_rr = acc[0];
       st->iter = it + 1;
     }
     st->inner_pp = pp + 2;
@@ -750,8 +758,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(cons
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const TlScal sc = tl_entry_scalars(P.cd, st);
   const int it = st->iter;
-  if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
+  if (st->comm_error || tl_should_stop(it, sc.rr, st->cfg)) return;
   const int pp = st->inner_pp;
   const bool last = (pp + 1 == st->inner_steps);
   const double alpha = P.alphas[pp], beta = P.betas[pp];
@@ -819,10 +828,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_ring(cons
     }
     tl_cp_wait<0>();
   }
-  if (tl_kernel_tail(acc, last, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, last, st, P.partials, P.cd, sm, TL_T_RR)) {
     if (last) {
       st->red_rr_local = acc[0];      // PPCG.jl:88
-      if (P.single || tiled) st->red_rr = acc[0];
+      if ((P.single || tiled) && !tl_is_deferred(P.cd)) st->red_rr = acc[0];
       st->iter = it + 1;
     }
     st->inner_pp = pp + 1;
@@ -841,8 +850,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_dk(const 
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const TlScal sc = tl_entry_scalars(P.cd, st);
   const int it = st->iter;
-  if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
+  if (st->comm_error || tl_should_stop(it, sc.rr, st->cfg)) return;
   const int pp = st->inner_pp, n = st->inner_steps, k = P.k;
   const int grp = pp / k, q = pp - grp * k, G = (n + k - 1) / k;
   const int L = min(k, n - grp * k);                 // steps in this group
@@ -935,10 +945,10 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_ppcg_inner_dk(const 
     }
     tl_cp_wait<0>();
   }
-  if (tl_kernel_tail(acc, last, st, P.partials, group_end ? P.cd : nullptr, sm)) {
+  if (tl_kernel_tail(acc, last, st, P.partials, group_end ? P.cd : nullptr, sm, TL_T_RR)) {
     if (last) {
       st->red_rr_local = acc[0];      // PPCG.jl:88
-      st->red_rr = acc[0];
+      if (!tl_is_deferred(P.cd)) st->red_rr = acc[0];
       st->iter = it + 1;
     }
     st->inner_pp = pp + 1;
@@ -953,8 +963,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_jacobi_fused_ring(co
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const TlScal sc = tl_entry_scalars(P.cd, st);
   const int it = st->iter;
-  if (st->comm_error || tl_should_stop(it, st->red_rr, st->cfg)) return;
+  if (st->comm_error || tl_should_stop(it, sc.rr, st->cfg)) return;
   const double *__restrict__ uin = (it & 1) ? P.ub : P.ua;
   double *__restrict__ uout = (it & 1) ? P.ua : P.ub;
   const bool tiled = P.cd != nullptr;
@@ -1021,9 +1032,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_jacobi_fused_ring(co
     }
     tl_cp_wait<0>();
   }
-  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm, TL_T_RR)) {
     st->red_rr_local = acc[0];
-    st->red_rr = acc[0];
+    if (!tl_is_deferred(P.cd)) st->red_rr = acc[0];
     st->iter = it + 1;
   }
 }
@@ -1036,6 +1047,7 @@ __global__ void __launch_bounds__(TL_BASIC_THREADS) k_jacobi_resid(const JacobiP
   __shared__ double sm[32];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  (void)tl_entry_scalars(P.cd, st);        // collect what the last iteration kernel posted (split exchange)
   const int it = st->iter;
   if (st->comm_error) return;
   if (!P.force_resid && (it == 0 || it % 50 != 0)) return;
@@ -1048,9 +1060,9 @@ __global__ void __launch_bounds__(TL_BASIC_THREADS) k_jacobi_resid(const JacobiP
     P.r[o] = rv;
     acc[0] += rv * rv;
   }
-  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm, P.force_resid ? TL_T_NONE : TL_T_RR)) {
     st->red_rr_local = acc[0];
-    if (!P.force_resid) st->red_rr = acc[0];
+    if (!P.force_resid && !tl_is_deferred(P.cd)) st->red_rr = acc[0];
   }
 }
 

@@ -56,8 +56,9 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_tma(const
   __shared__ __align__(8) unsigned long long bars[TL_FUSED_THREADS / 32][S];
   SolveState *st = P.st;
   tl_prof_entry(st);
+  const TlScal sc = tl_entry_scalars(P.cd, st);
   const int it = st->iter;
-  const double rr_cur = st->red_rr;
+  const double rr_cur = sc.rr;
   if (st->comm_error || tl_should_stop(it, rr_cur, st->cfg)) return;
   const bool first = (it == st->cfg.first_it);
   double beta = 0.0, alpha_prev = 0.0;
@@ -186,8 +187,8 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_tma(const
       Xm = Xc; Xc = Xn; XcE = XnE; pc = c_p; kyc = c_ky;
     }
   }
-  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm)) {
+  if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm, TL_T_PW)) {
     st->red_pw_local = acc[0];
-    if (P.single || P.cd != nullptr) st->red_pw = acc[0];
+    if ((P.single || P.cd != nullptr) && !tl_is_deferred(P.cd)) st->red_pw = acc[0];
   }
 }

@@ -188,3 +188,27 @@ def test_tiled_ppcg_pairs_match(grid, nx, ny, hd, inner):
     for f in fields:
         assert np.abs(base[2][f][hd:-hd, hd:-hd] - pair[2][f][hd:-hd, hd:-hd]).max() <= 1e-11 * scale, f
     check_against_oracle(pair, run_oracle("ppcg", nx, ny, over=over), "ppcg", hd=hd)
+
+
+# ---- split tile exchange: post in the kernel tail, collect at the next kernel's entry (option xchg_deferred) -----
+SPLIT_CASES = [((2, 2), "cg", 200, 150, {}), ((1, 4), "cg", 96, 256, {}), ((2, 2), "cheby", 129, 140, {}), ((3, 2), "cheby", 200, 131, {"halodepth": 3}),
+               ((2, 2), "ppcg", 131, 150, {"ppcginnersteps": 5}), ((2, 2), "ppcg", 160, 120, {"ppcginnersteps": 6, "ppcghalodepth": 2}),
+               ((2, 1), "ppcg", 130, 77, {"ppcginnersteps": 4, "ppcghalodepth": 1}), ((2, 2), "jacobi", 160, 130, {"maxiters": 120}),
+               ((2, 2), "cheby", 150, 131, {"maxiters": 57})]
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("grid,solver,nx,ny,over", SPLIT_CASES, ids=[f"{g[0]}x{g[1]}-{s}-{nx}x{ny}-{'-'.join(f'{k}{v}' for k, v in o.items())}" for g, s, nx, ny, o in SPLIT_CASES])
+def test_split_exchange_is_bit_identical(grid, solver, nx, ny, over):
+    """xchg_deferred = 1: the same packets, the same rank-order sums -- every field, iteration count and error value is
+    bit-identical to the blocking exchange, two timesteps (state carried over), and matches the oracle."""
+    fields = ("u", "energy", "p", "r", "sd")
+    hd = over.get("halodepth", 2)
+    base = run_tiled(grid, solver, nx, ny, steps=2, over=over, options={"xchg_deferred": 0}, fields=fields)
+    split = run_tiled(grid, solver, nx, ny, steps=2, over=over, options={"xchg_deferred": 1}, fields=fields)
+    key = lambda recs: [(r["iters"], r["cg_iters"], r["cheby_iters"], r["inner_total"], r["error"]) for r in recs]
+    assert key(base[0]) == key(split[0])
+    assert base[1] == split[1]
+    for f in fields:
+        np.testing.assert_array_equal(base[2][f][hd:-hd, hd:-hd], split[2][f][hd:-hd, hd:-hd], err_msg=f)
+    check_against_oracle(split, run_oracle(solver, nx, ny, steps=2, over=over), solver, hd=hd)
