@@ -113,6 +113,9 @@ int tl_abi_version(void);
  *   hint_keep, hint_stream, l2_persist_mb, l2_hit_scale, l2_persist_field    L2 policy experiments
  *   use_pdl                     programmatic dependent launch between the loop kernels, released before the kernel tails
  *   comm_fused                  tiles: 1 halo pushes + mailbox sums inside the kernels (default), 0 NCCL + pull kernels
+ *   xchg_deferred               tiles: split exchange -- kernels post their packets in the tail, the next kernel collects them at
+ *                               its entry (bit-identical; measured slower than the blocking exchange: default 0)
+ *   pair_stages                 cp.async ring depth of the pair kernels: 4 (default) or 5
  *   ppcg_halo_depth             tiles, one kernel per inner step: exchange every k steps (0 = automatic: the pair kernels,
  *                               i.e. every 2 steps, or every halo_depth steps when they are off)
  *   prof                        kernel-boundary micro-profile: globaltimer stamps in the kernel tails; read the averages per

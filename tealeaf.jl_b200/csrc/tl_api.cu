@@ -783,6 +783,7 @@ __global__ void k_tile_allreduce(const CommDev *cd, SolveState *st, const double
   __shared__ double sm[32];
   (void)tl_entry_scalars(cd, st);   // split exchange: collect what a loop kernel posted before exchanging again
   __syncthreads();
+  if (threadIdx.x == 0) st->pend_target = TL_T_NONE;   // consumed: whoever writes red_* next is not patched over
   if (st->comm_error) return;
   if (threadIdx.x == blockDim.x - 1) __threadfence_system();
   for (int q = 0; q < n; q++) {
@@ -794,7 +795,11 @@ __global__ void k_tile_allreduce(const CommDev *cd, SolveState *st, const double
 
 // Split exchange: publishes the total of the exchange the last loop kernel posted (nobody collected it yet) into the
 // SolveState.  Enqueued wherever the host, or a kernel that reads the SolveState directly, comes next.
-__global__ void k_xchg_finalize(const CommDev *cd, SolveState *st) { (void)tl_entry_scalars(cd, st); }
+__global__ void k_xchg_finalize(const CommDev *cd, SolveState *st) {
+  (void)tl_entry_scalars(cd, st);
+  __syncthreads();
+  if (threadIdx.x == 0) st->pend_target = TL_T_NONE;   // consumed: the SolveState holds the totals; later direct writers are not patched over
+}
 static bool xchg_deferred(const tl_ctx *c) { return c->nranks > 1 && c->comm_fused && c->xchg_deferred; }
 static int xchg_finalize(tl_ctx *c) {
   if (!xchg_deferred(c)) return TL_OK;

@@ -82,7 +82,9 @@ struct SolveState {
   // split tile exchange (CommDev::deferred): the exchange the previous kernel POSTED in its tail and that nobody has
   // collected yet -- number, which scalar it carries (TL_T_*), and the number of the last exchange block 0 of a later
   // kernel has published into red_pw / red_rr / red_norm
-  unsigned long long pend_seq, coll_seq;
+  unsigned long long pend_seq;
+  unsigned long long pub_lo, pub_hi;   // the last COLLECTED exchange as an LL packet (number | half of the total): block 0 of the
+                                       // collecting kernel publishes it, the other blocks read it with two loads and no fence
   int pend_target, pad3;
   // diagnostics of the last blocking exchange: where thread q sent its packet and what the slot it waited on held
   // when it gave up (reported with a time-out: tl_api.cu check_comm)
@@ -360,55 +362,70 @@ __device__ __forceinline__ void tl_tile_post(const CommDev *cd, SolveState *st, 
   }
 }
 
-// Kernel entry, every thread: the scalars this kernel works with -- the SolveState's, with the total of a posted and not
-// yet collected exchange patched in.  Returns with comm_error set if a tile never posted.
+// Kernel entry, every thread: the scalars this kernel works with -- the SolveState's, with the total of the exchange
+// the previous kernel posted patched in.  Fast path (all blocks but the earliest): block 0 has already collected the
+// packets and published the total as an LL packet in the SolveState -- everything needed comes from ONE batch of
+// independent loads, no fence, no polling.  Slow path (blocks that start before that): poll the n mailbox slots
+// themselves (every block would have to wait for the slowest tile anyway) and add them in rank order -- the same bits.
+__device__ __forceinline__ unsigned long long tl_ld_acquire_gpu(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ TlScal tl_entry_scalars(const CommDev *cd, SolveState *st) {
   TlScal S;
   if (!tl_is_deferred(cd)) {
     S.pw = st->red_pw; S.rr = st->red_rr; S.norm = st->red_norm;
     return S;
   }
+  // one batch of independent loads (the tail of the previous kernel wrote pend_*; block 0 of THIS kernel may be writing pub_* / red_*)
   const unsigned long long pseq = *(volatile unsigned long long *)&st->pend_seq;
-  const unsigned long long cseq = *(volatile unsigned long long *)&st->coll_seq;
-  __threadfence();   // block 0 publishes the totals, fences, then sets coll_seq: read in the opposite order
+  const int target = *(volatile int *)&st->pend_target;
+  const unsigned long long plo = tl_ld_relaxed_sys(&st->pub_lo);
+  const unsigned long long phi = tl_ld_acquire_gpu(&st->pub_hi);   // acquire: the halo loads below are ordered after the publication
   S.pw = *(volatile double *)&st->red_pw; S.rr = *(volatile double *)&st->red_rr; S.norm = *(volatile double *)&st->red_norm;
-  if (pseq == cseq) return S;     // nothing pending, or block 0 of this kernel has published it already
-  const bool prof = st->prof != 0 && blockIdx.x == 0 && threadIdx.x == 0;
-  const unsigned long long tp = prof ? tl_globaltimer() : 0;
-  const int n = (int)tl_ld_relaxed_sys((const unsigned long long *)&cd->nranks);
-  const int my_rank = (int)(tl_ld_relaxed_sys((const unsigned long long *)&cd->nranks) >> 32);
   const unsigned seq = (unsigned)pseq;
-  const MailSlot *box = (const MailSlot *)tl_ld_relaxed_sys((const unsigned long long *)&cd->mail[my_rank]) + (seq & 1u) * TL_MAX_RANKS;
-  double total = 0.0;
-  unsigned long long t0 = 0;
-  for (int r = 0; r < n; r++) {          // warp-uniform addresses: one L2 transaction per warp and load
-    unsigned long long lo, hi;
-    unsigned spins = 0;
-    for (;;) {
-      lo = tl_ld_relaxed_sys(&box[r].lo);
-      hi = tl_ld_relaxed_sys(&box[r].hi);
-      if ((unsigned)(lo >> 32) == seq && (unsigned)(hi >> 32) == seq) break;
-      if ((++spins & 1023u) == 0u) {
-        const unsigned long long t = tl_globaltimer();
-        if (t0 == 0) t0 = t;
-        else if (t - t0 > TL_XCHG_TIMEOUT_NS) { st->comm_error = 1 + r; return S; }
+  double total;
+  if ((unsigned)(plo >> 32) == seq && (unsigned)(phi >> 32) == seq) {
+    total = __longlong_as_double((long long)((plo & 0xffffffffull) | (phi << 32)));      // collected already: by block 0, or by an earlier kernel
+  } else {
+    const bool prof = st->prof != 0 && blockIdx.x == 0 && threadIdx.x == 0;
+    const unsigned long long tp = prof ? tl_globaltimer() : 0;
+    const int n = (int)tl_ld_relaxed_sys((const unsigned long long *)&cd->nranks);
+    const int my_rank = (int)(tl_ld_relaxed_sys((const unsigned long long *)&cd->nranks) >> 32);
+    const MailSlot *box = (const MailSlot *)tl_ld_relaxed_sys((const unsigned long long *)&cd->mail[my_rank]) + (seq & 1u) * TL_MAX_RANKS;
+    total = 0.0;
+    unsigned long long t0 = 0;
+    for (int r = 0; r < n; r++) {          // warp-uniform addresses: one L2 transaction per warp and load
+      unsigned long long lo, hi;
+      unsigned spins = 0;
+      for (;;) {
+        lo = tl_ld_relaxed_sys(&box[r].lo);
+        hi = tl_ld_relaxed_sys(&box[r].hi);
+        if ((unsigned)(lo >> 32) == seq && (unsigned)(hi >> 32) == seq) break;
+        if ((++spins & 1023u) == 0u) {
+          const unsigned long long t = tl_globaltimer();
+          if (t0 == 0) t0 = t;
+          else if (t - t0 > TL_XCHG_TIMEOUT_NS) { st->comm_error = 1 + r; return S; }
+        }
       }
+      total += __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
     }
-    total += __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    (void)tl_ld_acquire_sys(&box[0].hi);   // acquire: the halo loads below see what the tiles pushed before posting
+    if (blockIdx.x == 0 && threadIdx.x == 0) {     // publish: for the later blocks of this kernel, for later kernels, for the host
+      if (target == TL_T_PW) st->red_pw = total;
+      else if (target == TL_T_RR) st->red_rr = total;
+      else if (target == TL_T_NORM) st->red_norm = total;
+      __threadfence();
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
+      tl_st_relaxed_sys(&st->pub_lo, ((unsigned long long)seq << 32) | (bits & 0xffffffffull));
+      tl_st_relaxed_sys(&st->pub_hi, ((unsigned long long)seq << 32) | (bits >> 32));
+      if (prof) st->prof_acc[2] += tl_globaltimer() - tp;
+    }
   }
-  (void)tl_ld_acquire_sys(&box[0].hi);   // acquire: the halo loads below see what the tiles pushed before posting
-  const int target = st->pend_target;
   if (target == TL_T_PW) S.pw = total;
   else if (target == TL_T_RR) S.rr = total;
   else if (target == TL_T_NORM) S.norm = total;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {     // for the host and for kernels that read the SolveState directly
-    if (target == TL_T_PW) st->red_pw = total;
-    else if (target == TL_T_RR) st->red_rr = total;
-    else if (target == TL_T_NORM) st->red_norm = total;
-    __threadfence();
-    *(volatile unsigned long long *)&st->coll_seq = pseq;
-    if (prof) st->prof_acc[2] += tl_globaltimer() - tp;
-  }
   return S;
 }
 
