@@ -7,7 +7,6 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
@@ -17,7 +16,10 @@ from tealeaf_jl_b200.device import DeviceChunk  # noqa: E402
 
 CASES = [("cg", 97, 61, {}, {}), ("cg", 130, 40, {}, {"cg_persist": 1}), ("cg", 75, 90, {}, {"b_ring": 6}),
          ("cg", 64, 33, {}, {"b_ring": 8}), ("cheby", 97, 61, {}, {}), ("ppcg", 97, 61, {"ppcginnersteps": 4}, {}),
-         ("jacobi", 50, 45, {"maxiters": 120}, {}), ("cg", 1, 40, {}, {}), ("cg", 200, 3, {"halodepth": 3}, {})]
+         ("jacobi", 50, 45, {"maxiters": 120}, {}), ("cg", 1, 40, {}, {}), ("cg", 200, 3, {"halodepth": 3}, {}),
+         # round 2: TMA ring of kernel A, odd PPCG inner count (pairs + trailing step), 5-slot pair ring, Chebyshev pairs
+         ("cg", 130, 70, {}, {"a_tma": 4}), ("cg", 63, 40, {}, {"a_tma": 3}), ("ppcg", 97, 61, {"ppcginnersteps": 5}, {}),
+         ("cheby", 130, 70, {}, {"pair_stages": 5}), ("ppcg", 70, 90, {"ppcginnersteps": 6}, {"pair_stages": 5})]
 
 
 def main():
