@@ -552,6 +552,8 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "pair_tiled") c->pair_tiled = value != 0.0;
   else if (n == "pair_rows") c->pair_rows = std::max(2, (int)value);
   else if (n == "pair_stages") {
+    // (3 slots at three CTAs per SM was measured too: 80 registers force spills, 91 -> 144 us per iteration at 4096^2:
+    // profiles/r02o_pair_stages_ab.log -- not kept)
     if ((int)value != 4 && (int)value != 5) return tl_fail(c, TL_ERR_ARG, "pair_stages must be 4 or 5");
     c->pair_stages = (int)value;
   }
