@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <unistd.h>
 #ifdef TL_WITH_NCCL
 #include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
@@ -176,14 +178,14 @@ static cudaError_t tl_launch(tl_ctx *c, void (*kern)(const P), int grid, int blo
 // by 10-16 % (28 KB of L1 instead of 60 KB for the edge and prologue loads), so each kernel keeps its own split.
 static const bool g_same_carveout = getenv("TEALEAF_B200_CARVEOUT") && atoi(getenv("TEALEAF_B200_CARVEOUT")) == 1;
 template <typename P>
-static int tl_prepare_smem(tl_ctx *c, void (*kern)(const P), int smem, unsigned long long *device_mask) {
+static int tl_prepare_smem(tl_ctx *c, void (*kern)(const P), int smem, std::atomic<unsigned long long> *device_mask) {
   const unsigned long long bit = 1ull << (c->device & 63);
-  if (!(*device_mask & bit)) {
+  if (!(device_mask->load() & bit)) {   // tiles of one process prepare from several service threads: idempotent, the mask is atomic
     if (smem > 0) CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // every kernel of the iteration loops asks for the SAME L1 / shared-memory split (all shared): two consecutive
     // kernels with different carve-outs make the SMs reconfigure between them, which lengthens the launch gap
     if (g_same_carveout) CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    *device_mask |= bit;
+    device_mask->fetch_or(bit);
   }
   return TL_OK;
 }
@@ -363,7 +365,13 @@ static int multi_tile_offset(const tl_ctx *c, int idx, int *x0, int *y0);
 
 extern "C" int tl_abi_version(void) { return TL_ABI_VERSION; }
 
-static std::string g_create_error;   // why the last tl_create* call of the process failed (there is no context to ask then)
+// why the last tl_create* call of the process failed (there is no context to ask then); tiles are created from several threads
+static std::string g_create_error;
+static std::mutex g_create_error_mu;
+static void set_create_error(const std::string &msg) {
+  std::lock_guard<std::mutex> lk(g_create_error_mu);
+  g_create_error = msg;
+}
 extern "C" const char *tl_last_error(const tl_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int tl_set_option(tl_ctx *c, const char *name, double value);
@@ -419,7 +427,7 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
   c->slab_bytes = bytes;
   cudaError_t e = cudaMalloc((void **)&c->slab, bytes);
   if (e != cudaSuccess) {
-    g_create_error = cudaGetErrorString(e);
+    set_create_error(cudaGetErrorString(e));
     delete c;
     return TL_ERR_CUDA;
   }
@@ -443,7 +451,7 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
       cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess ||
       cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess ||
       cudaEventCreate(&c->ev_phase) != cudaSuccess) {
-    g_create_error = cudaGetErrorString(cudaGetLastError());
+    set_create_error(cudaGetErrorString(cudaGetLastError()));
     tl_destroy(c);
     return TL_ERR_CUDA;
   }
@@ -472,7 +480,7 @@ extern "C" int tl_create_tile(tl_ctx **out, int xcells, int ycells, int halo_dep
       const size_t eq = kv.find('=');
       if (kv.empty()) continue;
       if (eq == std::string::npos || tl_set_option(c, kv.substr(0, eq).c_str(), atof(kv.c_str() + eq + 1)) != TL_OK) {
-        g_create_error = "bad TEALEAF_B200_OPTS entry: " + kv;
+        set_create_error("bad TEALEAF_B200_OPTS entry: " + kv);
         tl_destroy(c);
         *out = nullptr;
         return TL_ERR_ARG;
@@ -1297,7 +1305,7 @@ static CgBParams cg_b_params(tl_ctx *c) {
 template <bool U, int S, int MINB>
 static int launch_ring(tl_ctx *c, const CgAParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_cg_fused_w_ring<U, S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_cg_fused_w_ring<U, S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
@@ -1338,7 +1346,7 @@ static int launch_cg_a_tma(tl_ctx *c, const CgAParams &A) {
   P.a = A;
   memcpy(P.maps, c->tma_maps, sizeof P.maps);
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_TMA_STAGE_BYTES;
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_cg_fused_w_tma<U, S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_cg_fused_w_tma<U, S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
@@ -1366,7 +1374,7 @@ static int launch_cg_a(tl_ctx *c) {
 template <bool FIRST, int S, int MINB>
 static int launch_cheby_ring(tl_ctx *c, const ChebyParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_cheby_fused_ring<FIRST, S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_cheby_fused_ring<FIRST, S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
@@ -1387,7 +1395,7 @@ static int launch_cheby(tl_ctx *c) {
 template <int S, int MINB>
 static int launch_ppcg_inner_ring(tl_ctx *c, const PpcgInnerParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_ppcg_inner_ring<S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_ppcg_inner_ring<S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
@@ -1409,7 +1417,7 @@ static int launch_ppcg_inner(tl_ctx *c) {
 template <int D, int MINB>
 static int launch_b_ring(tl_ctx *c, const CgBParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * D * TL_BRING_ROW_BYTES;
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_cg_fused_r_ring<D, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_cg_fused_r_ring<D, MINB>, c->pw_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
@@ -1418,7 +1426,7 @@ static int launch_cg_b(tl_ctx *c) {
   const CgBParams P = cg_b_params(c);
   switch (c->b_ring) {
     case 0: {
-      static unsigned long long prepared = 0;
+      static std::atomic<unsigned long long> prepared{0};
       TRY(tl_prepare_smem(c, k_cg_fused_r, 0, &prepared));
       CU(c, tl_launch(c, k_cg_fused_r, c->pw_grid, TL_FUSED_THREADS, 0, P));
       break;
@@ -1523,7 +1531,7 @@ static int solve_preamble(tl_ctx *c, int coef, double rx, double ry, const StopC
 template <int S, int MINB>
 static int launch_cg_persist(tl_ctx *c, const CgPersistParams &P0) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_cg_persist<S, MINB>, smem, &prepared));
   int per_sm = 0;
   CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persist<S, MINB>, TL_FUSED_THREADS, smem));
@@ -1688,7 +1696,7 @@ static bool cheby_pairs_tiled(const tl_ctx *c) { return c->cheby_pair && pairs_o
 template <int S, int MINB, bool TILED>
 static int launch_cheby_pair_ring(tl_ctx *c, const ChebyPairParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_cheby_pair_ring<S, MINB, TILED>, smem, &prepared));
   CU(c, tl_launch(c, k_cheby_pair_ring<S, MINB, TILED>, c->pair_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
@@ -1885,7 +1893,7 @@ static PpcgDkParams ppcg_dk_params(tl_ctx *c) {
 template <int S, int MINB>
 static int launch_ppcg_dk_ring(tl_ctx *c, const PpcgDkParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_ppcg_inner_dk<S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_ppcg_inner_dk<S, MINB>, c->dk_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
@@ -1926,7 +1934,7 @@ static bool ppcg_pairs_enabled(const tl_ctx *c, int inner_steps, int requested_d
 template <int S, int MINB, bool TILED>
 static int launch_ppcg_pair_ring(tl_ctx *c, const PpcgPairParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_ppcg_pair_ring<S, MINB, TILED>, smem, &prepared));
   CU(c, tl_launch(c, k_ppcg_pair_ring<S, MINB, TILED>, c->pair_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;
@@ -1976,7 +1984,7 @@ static int launch_ppcg_trailing(tl_ctx *c, int npairs) {
 }
 
 static int prepare_ur_sd(tl_ctx *c) {
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   return tl_prepare_smem(c, k_ppcg_ur_sd, 0, &prepared);
 }
 static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k, bool pairs) {
@@ -2182,7 +2190,7 @@ static JacobiParams jacobi_params(tl_ctx *c, int force_resid) {
 template <int S, int MINB>
 static int launch_jacobi_ring(tl_ctx *c, const JacobiParams &P) {
   const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
-  static unsigned long long prepared = 0;
+  static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_jacobi_fused_ring<S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_jacobi_fused_ring<S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
   return TL_OK;

@@ -170,7 +170,7 @@ extern "C" int tl_create_multi(tl_ctx **out, int xcells, int ycells, int halo_de
     py = ngpus / px;
   }
   if (px * py != ngpus || px > xcells || py > ycells) {
-    g_create_error = "tl_create_multi: px*py must equal ngpus and every tile needs at least one cell";
+    set_create_error("tl_create_multi: px*py must equal ngpus and every tile needs at least one cell");
     return TL_ERR_ARG;
   }
   int ndev = 0;
@@ -179,7 +179,7 @@ extern "C" int tl_create_multi(tl_ctx **out, int xcells, int ycells, int halo_de
   bool shared = false;
   for (int i = 0; i < ngpus; i++) {
     dev[i] = devices ? devices[i] : i;
-    if (dev[i] < 0 || dev[i] >= ndev) { g_create_error = "tl_create_multi: device index out of range"; return TL_ERR_NO_DEVICE; }
+    if (dev[i] < 0 || dev[i] >= ndev) { set_create_error("tl_create_multi: device index out of range"); return TL_ERR_NO_DEVICE; }
     for (int q = 0; q < i; q++) shared = shared || dev[q] == dev[i];
   }
   if (shared) {
@@ -187,8 +187,8 @@ extern "C" int tl_create_multi(tl_ctx **out, int xcells, int ycells, int halo_de
     // nothing may synchronise the device while they run -- lazy module loading does, on a kernel's first launch
     const char *ml = getenv("CUDA_MODULE_LOADING");
     if (!ml || std::string(ml) != "EAGER") {
-      g_create_error = "tl_create_multi: tiles that share a GPU need CUDA_MODULE_LOADING=EAGER (and CUDA_DEVICE_MAX_CONNECTIONS >= "
-                       "the number of tiles) set before CUDA initialises";
+      set_create_error("tl_create_multi: tiles that share a GPU need CUDA_MODULE_LOADING=EAGER (and CUDA_DEVICE_MAX_CONNECTIONS >= "
+                       "the number of tiles) set before CUDA initialises");
       return TL_ERR_STATE;
     }
   }
@@ -217,7 +217,7 @@ extern "C" int tl_create_multi(tl_ctx **out, int xcells, int ycells, int halo_de
     rc = tl_comm_connect(m->tiles[0], nullptr, nullptr);
   }
   if (rc != TL_OK) {
-    g_create_error = c->err.empty() ? g_create_error : c->err;
+    set_create_error(c->err.empty() ? g_create_error : c->err);
     multi_destroy(c);
     return rc;
   }
