@@ -19,7 +19,7 @@ from .settings import Settings, State, parse_settings, parse_settings_text, chec
 from .settings import CONDUCTIVITY, RECIP_CONDUCTIVITY, EXCHANGE_FIELDS  # noqa: F401
 from .chunk import HostGeometry, paint_states, FIELD_NAMES, FIELD_IDS  # noqa: F401
 from .solvers import CG, Cheby, PPCG, get_solver, haloupdate  # noqa: F401
-from .app import initialiseapp, diffuse, fieldsummary, upload_initial_state  # noqa: F401
+from .app import initialiseapp, diffuse, fieldsummary, upload_initial_state, write_tea_out  # noqa: F401
 
 
 def DeviceChunk(*a, **kw):

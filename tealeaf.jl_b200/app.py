@@ -119,6 +119,36 @@ def debugrecord(settings: Settings, chunk, geom: HostGeometry):
         fh.write("\n\n")
 
 
+def write_tea_out(path, settings: Settings, records, final, wall_s=None):
+    """`tea.out`-style report: the reference only logs (`@info`, src/TeaLeaf.jl:80,
+    src/kernels.jl:125-131); upstream TeaLeaf writes this table.  One block per timestep (solver, iterations,
+    error), the four-component field summary where one was taken, the QA verdict at the end."""
+    head = f"{'':>12}{'Volume':>16}{'Mass':>16}{'Density':>16}{'Energy':>16}{'U':>16}"
+
+    def row(tag, s):
+        dens = s["mass"] / s["vol"] if s["vol"] else 0.0
+        return f"{tag:>12}{s['vol']:16.7E}{s['mass']:16.7E}{dens:16.7E}{s['ie']:16.7E}{s['temp']:16.7E}"
+
+    lines = ["Tea Version libtealeaf_b200", f" Mesh {settings.xcells} x {settings.ycells}, solver {settings.solver}, "
+             f"dt {settings.dtinit!r}, eps {settings.eps!r}, max_iters {settings.maxiters}", ""]
+    for r in records:
+        lines.append(f" Step {r['step']:7d} time {r['step'] * settings.dtinit:.7E} timestep {settings.dtinit:.7E}")
+        extra = "".join(f", {k} {r[k]}" for k in ("cheby_iters", "inner_total", "est_iters") if r.get(k))
+        lines.append(f" Conduction error {r.get('error', 0.0):.7E}")
+        lines.append(f" Iteration count {r.get('iters', 0):8d}{extra}")
+        if "summary" in r:
+            lines += ["", head, row(f"step:{r['step']:7d}", r["summary"]), ""]
+    lines += ["", head, row("final:", final), ""]
+    if "cv" in final:
+        lines.append(f" Checking results... expected {final['cv']:.15E} got {final['temp']:.15E} "
+                     f"diff {final['qa_diff']:.7E} %")
+        lines.append(" This test is considered PASSED" if final["passed"] else " This test is considered NOT PASSED")
+    if wall_s is not None:
+        lines.append(f" Wall clock {wall_s:.6f} s")
+    with open(path, "w", encoding="utf-8") as fh:
+        fh.write("\n".join(lines) + "\n")
+
+
 def diffuse(chunk, settings: Settings, geom: HostGeometry, stepwise: bool = False, on_step=None):
     """`diffuse!`, src/TeaLeaf.jl:62-83.  Returns the per-step records."""
     if settings.endstep >= 2**62:

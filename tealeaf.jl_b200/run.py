@@ -1,14 +1,16 @@
 """CLI -- mirror of the reference's `run.jl` (same flags, `run.jl:5-23`).
 
-    python -m tealeaf_jl_b200.run -i decks/tea_bm_small.in [-s cg|cheby|ppcg] [-x N] [-y N] [--stepwise]
+    python -m tealeaf_jl_b200.run -i decks/tea_bm_small.in [-s cg|cheby|ppcg|jacobi] [-x N] [-y N] [-O dump]
+                                  [--gpus N] [--tea-out tea.out] [--stepwise]
 """
 from __future__ import annotations
 
 import argparse
 import json
 import logging
+import time
 
-from .app import diffuse, initialiseapp
+from .app import diffuse, initialiseapp, write_tea_out
 from .settings import parse_settings
 
 
@@ -22,6 +24,8 @@ def main(argv=None):
     ap.add_argument("-O", "--debug-out", help="File to print debug state to")  # run.jl:20-22
     ap.add_argument("--stepwise", action="store_true", help="drive the solve kernel by kernel (per-function ABI)")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--gpus", type=int, default=1, help="spread the one Chunk over N GPUs of this process (tl_create_multi)")
+    ap.add_argument("--tea-out", help="write an upstream-style tea.out report (steps, iterations, field summaries, QA)")
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO, format="%(message)s")
     settings = parse_settings(args.in_file)                                # run.jl:26
@@ -34,8 +38,15 @@ def main(argv=None):
     if args.debug_out:
         settings.debugfile = args.debug_out                                # run.jl:41-43
     settings.recompute_spacing()                                           # Appendix A #23
-    chunk, geom = initialiseapp(settings, device=args.device)              # run.jl:45
+    t0 = time.perf_counter()
+    if args.gpus > 1:
+        from .device import DeviceChunk
+        chunk, geom = initialiseapp(settings, backend=DeviceChunk.multi, ngpus=args.gpus)
+    else:
+        chunk, geom = initialiseapp(settings, device=args.device)          # run.jl:45
     records, final = diffuse(chunk, settings, geom, stepwise=args.stepwise)  # run.jl:47
+    if args.tea_out:
+        write_tea_out(args.tea_out, settings, records, final, time.perf_counter() - t0)
     for r in records:
         print(json.dumps({k: v for k, v in r.items() if k != "summary"}))
     print(json.dumps({"final_summary": final}))

@@ -63,3 +63,28 @@ def test_c_host_matches_the_python_mirror_and_the_oracle(tmp_path, solver, nx, n
             assert abs(rec["iters"] - iters) <= slack, (backend.__name__, rec["iters"], iters)
         for name, got in zip(("vol", "mass", "ie", "temp"), summary):
             assert abs(got - final[name]) <= tol * abs(final[name]), (backend.__name__, name, got, final[name])
+
+
+@pytest.mark.gpu
+def test_python_cli_mirror_of_run_jl(tmp_path, capsys):
+    """`run.py` = run.jl (same flags, run.jl:5-23): deck from -i, -s / -x / -y overrides, -O dump, plus the tea.out
+    report; the final summary equals the oracle's."""
+    import json
+    from tealeaf_jl_b200 import run as cli
+    from oracle.oracle import OracleChunk
+    deck = os.path.join(ROOT, "decks", "tea_bm_small.in")
+    out, dump = tmp_path / "tea.out", tmp_path / "dump.txt"
+    cli.main(["-i", deck, "-s", "cheby", "-x", "128", "-y", "96", "-O", str(dump), "--tea-out", str(out)])
+    lines = [json.loads(ln) for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    final = lines[-1]["final_summary"]
+    s = tl.parse_settings(deck)
+    s.solver, s.xcells, s.ycells = "cheby", 128, 96
+    s.recompute_spacing()
+    chunk, geom = tl.initialiseapp(s, backend=OracleChunk)
+    recs, ofinal = tl.diffuse(chunk, s, geom)
+    assert [ln["iters"] for ln in lines[:-1]] == [r["iters"] for r in recs] and lines[0]["cheby_iters"] > 0
+    for k in ("vol", "mass", "ie", "temp"):
+        assert abs(final[k] - ofinal[k]) <= 1e-10 * abs(ofinal[k]), k
+    text = out.read_text()
+    assert text.count(" Step ") == 2 and "final:" in text and "solver cheby" in text
+    assert dump.read_text().count("density0\n") == 2          # one record per timestep (TeaLeaf.jl:68)

@@ -225,3 +225,21 @@ def test_end_time_ends_the_timestep_loop():
     chunk2, geom2 = tl.initialiseapp(s2, backend=OracleChunk)
     recs2, final2 = tl.diffuse(chunk2, s2, geom2)
     assert [r["iters"] for r in recs] == [r["iters"] for r in recs2] and final["temp"] == final2["temp"]
+
+
+def test_tea_out_report(tmp_path):
+    """`tea.out`-style report: every step, the four-component summaries, the QA verdict."""
+    s = classic_settings(10, 10, steps=2, solver="cg")
+    s.checkresult = True
+    s.summaryfrequency = 1
+    chunk, geom, recs, final = run_oracle(s)
+    path = tmp_path / "tea.out"
+    tl.write_tea_out(str(path), s, recs, final, wall_s=0.5)
+    text = path.read_text()
+    assert text.count(" Step ") == 2 and text.count("step:") == 2 and "final:" in text
+    for r in recs:
+        assert f" Iteration count {r['iters']:8d}" in text
+    last = [ln for ln in text.splitlines() if ln.lstrip().startswith("final:")][0].split()
+    assert float(last[1]) == pytest.approx(final["vol"], rel=1e-7) and float(last[5]) == pytest.approx(final["temp"], rel=1e-7)
+    assert float(last[3]) == pytest.approx(final["mass"] / final["vol"], rel=1e-7)
+    assert ("This test is considered PASSED" in text) == bool(final["passed"])
