@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu
 import emulate_pair  # noqa: E402
 import emulate_ppcg_pair  # noqa: E402
 import emulate_pair_tiled  # noqa: E402
+import emulate_ppcg_pair_tiled  # noqa: E402
 
 
 @pytest.mark.parametrize("nx,ny,rows", emulate_pair.CASES)
@@ -26,8 +27,8 @@ def test_ppcg_pair_window_logic(nx, ny, rows):
 
 @pytest.mark.parametrize("NX,NY,px,py,rows", emulate_pair_tiled.CASES)
 def test_tiled_pair_design_halo_depths_are_sufficient(NX, NY, px, py, rows):
-    """Next step of DESIGN.md section 7: the same window kernel on px x py tiles with u two cells deep (corners
-    included), p / u0 one deep and kx / ky two deep in the tile-internal halos reproduces the single chunk."""
+    """the same window kernel on px x py tiles with u two cells deep (corners included),
+    p / u0 one deep and kx / ky two deep in the tile-internal halos reproduces the single chunk."""
     assert emulate_pair_tiled.run(NX, NY, px, py, rows)
 
 
@@ -35,3 +36,15 @@ def test_tiled_pair_design_halo_depths_are_necessary():
     assert not emulate_pair_tiled.run(130, 12, 2, 2, 3, du=1)
     assert not emulate_pair_tiled.run(130, 12, 2, 2, 3, dp=0)
     assert not emulate_pair_tiled.run(130, 12, 2, 2, 3, dk=1)
+
+
+@pytest.mark.parametrize("NX,NY,px,py,rows", emulate_ppcg_pair_tiled.CASES)
+def test_tiled_ppcg_pair_design_halo_depths_are_sufficient(NX, NY, px, py, rows):
+    """k_ppcg_pair_ring on tiles: sd two cells deep (corners included), r one deep, kx / ky two deep, nothing of u."""
+    assert emulate_ppcg_pair_tiled.run(NX, NY, px, py, rows)
+
+
+def test_tiled_ppcg_pair_design_halo_depths_are_necessary():
+    assert not emulate_ppcg_pair_tiled.run(130, 12, 2, 2, 3, ds=1)
+    assert not emulate_ppcg_pair_tiled.run(130, 12, 2, 2, 3, dr=0)
+    assert not emulate_ppcg_pair_tiled.run(130, 12, 2, 2, 3, dk=1)
