@@ -41,6 +41,7 @@ UNIT = "cell-iterations/s"
 CG_ALG_BYTES = 104          # w! 32 + ur! 48 + p! 24 bytes per cell-iteration
 KERNEL_A_ALG_BYTES = 80     # k_cg_fused_w covers w! (32) + p! (24) + the u half of ur! (24)
 KERNEL_A_PHYS_BYTES = 64    # what it physically moves: read r,p,u,kx,ky; write p,u,w
+KERNEL_A_PHYS_BYTES_LAZY = 60   # u advanced every second launch with both pending updates: 72 / 48 B, 60 on average
 KERNEL_B_ALG_BYTES = 24     # k_cg_fused_r: the r half of ur!
 
 
@@ -452,17 +453,25 @@ def run_b200(args):
     # ---- dominant kernel in isolation (state is scratch from here on) ----
     peak, peak_src = measured_peaks()
     tile_cells = tile_nx * tile_ny
-    ka_ms = chunk.time_kernel("cg_fused_w", 30)
+    # kernel A advances u every second launch (option cg_lazy_u, default): launches alternate between two costs, so the
+    # average launch is the mean of the two (tl_time_kernel "cg_fused_w" = a launch with the u update, "_odd" = without)
+    lazy_u = int(chunk.get_option("cg_u_mode")) == 2
+    ka_upd_ms = chunk.time_kernel("cg_fused_w", 30)
+    ka_odd_ms = chunk.time_kernel("cg_fused_w_odd", 30) if lazy_u else ka_upd_ms
+    ka_ms = 0.5 * (ka_upd_ms + ka_odd_ms)
     kb_ms = chunk.time_kernel("cg_fused_r", 30)
     it_ms = solve_ms / max(iters, 1)
-    traffic = TRAFFIC.get(f"k_cg_fused_w@{tile_nx}x{tile_ny}")      # ncu dram bytes per launch at this tile size, or None
+    a_phys = KERNEL_A_PHYS_BYTES_LAZY if lazy_u else KERNEL_A_PHYS_BYTES
+    # ncu dram bytes per launch at this tile size (lazy: mean of the two kinds of launch), or None
+    traffic = TRAFFIC.get(f"k_cg_fused_w{'_lazy' if lazy_u else ''}@{tile_nx}x{tile_ny}")
     roofline = {
-        "bound": "hbm", "kernel": "k_cg_fused_w_ring<true, S, MINB> (CG kernel A)",
+        "bound": "hbm", "kernel": "k_cg_fused_w_ring<UM, S, MINB> (CG kernel A" + (", u advanced every second launch)" if lazy_u else ")"),
         "achieved": KERNEL_A_ALG_BYTES * tile_cells / (ka_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": KERNEL_A_ALG_BYTES * tile_cells / (ka_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
         "peak_source": peak_src, "avg_launch_ms": ka_ms,
-        "algorithmic_bytes_per_cell": KERNEL_A_ALG_BYTES, "physical_bytes_per_cell": KERNEL_A_PHYS_BYTES,
-        "physical_gbs": KERNEL_A_PHYS_BYTES * tile_cells / (ka_ms * 1e-3) / 1e9,
+        "launch_ms_with_u_update": ka_upd_ms, "launch_ms_without_u_update": ka_odd_ms,
+        "algorithmic_bytes_per_cell": KERNEL_A_ALG_BYTES, "physical_bytes_per_cell": a_phys,
+        "physical_gbs": a_phys * tile_cells / (ka_ms * 1e-3) / 1e9,
         "other_kernels": {"k_cg_fused_r": {"avg_launch_ms": kb_ms,
                                            "achieved": KERNEL_B_ALG_BYTES * tile_cells / (kb_ms * 1e-3) / 1e9}},
         "iteration": {"ms": it_ms, "algorithmic_bytes_per_cell": CG_ALG_BYTES,

@@ -137,6 +137,7 @@ struct tl_ctx {
   CUtensorMap tma_maps[TMA_NMAPS];
   bool tma_ready = false;
   int b_ring = 0;           // kernel B flavour: 0 = register batches of 4 rows; 6 / 8 = cp.async ring of that depth (4 / 3 CTAs per SM)
+  int cg_lazy_u = 0;        // 1: kernel A of the CG loop advances u every second launch (TL_U_LAZY, tl_kernels_ring.cuh)
   int cg_persist = 0;       // 1: the CG loop of a single tile runs as ONE persistent cooperative kernel (tl_kernels_persist.cuh)
   PersistSync *psync = nullptr;
   int comm_fused = 1;       // 1: halo pushes + mailbox allreduce inside the kernels; 0: halo-pull kernels + NCCL
@@ -374,6 +375,12 @@ static void set_create_error(const std::string &msg) {
 }
 extern "C" const char *tl_last_error(const tl_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
+// How the CG loop's kernel A advances u: every second launch (TL_U_LAZY, the default) unless a flavour without that
+// mode is selected (TMA ring, persistent kernel)
+static int cg_u_mode(const tl_ctx *c) {
+  return (c->cg_lazy_u && !c->a_tma && !(c->cg_persist && c->nranks == 1)) ? TL_U_LAZY : TL_U_EVERY;
+}
+
 extern "C" int tl_set_option(tl_ctx *c, const char *name, double value);
 extern "C" void tl_destroy(tl_ctx *c);
 
@@ -549,6 +556,7 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   }
   else if (n == "use_pdl") c->use_pdl = value != 0.0;   // programmatic dependent launch, released before the kernel tails (tl_pdl_trigger)
   else if (n == "cg_persist") c->cg_persist = value != 0.0;
+  else if (n == "cg_lazy_u") c->cg_lazy_u = value != 0.0;
   else if (n == "a_tma") {   // 0 off; 1 / 4: TMA ring of 4 row slots; 3: of 3 row slots (two CTAs per SM either way)
     const int d = (int)value;
     if (d != 0 && d != 1 && d != 3 && d != 4) return tl_fail(c, TL_ERR_ARG, "a_tma must be 0, 1, 3 or 4");
@@ -625,6 +633,8 @@ extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
   else if (n == "xchg_deferred") v = c->xchg_deferred;
   else if (n == "use_pdl") v = c->use_pdl;
   else if (n == "cg_persist") v = c->cg_persist;
+  else if (n == "cg_lazy_u") v = c->cg_lazy_u;
+  else if (n == "cg_u_mode") v = cg_u_mode(c);
   else if (n == "a_tma") v = c->a_tma;
   else if (n == "balanced_tiling") v = c->balanced_tiling;
   else if (n == "cheby_pair") v = c->cheby_pair;
@@ -1302,9 +1312,9 @@ static CgBParams cg_b_params(tl_ctx *c) {
 }
 
 // kernel A in the configured flavour (register double-buffering or cp.async ring)
-template <bool U, int S, int MINB>
+template <int U, int S, int MINB>
 static int launch_ring(tl_ctx *c, const CgAParams &P) {
-  const int smem = (TL_FUSED_THREADS / 32) * S * TL_RING_STAGE_BYTES;
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_CGA_STAGE_BYTES(U);
   static std::atomic<unsigned long long> prepared{0};
   TRY(tl_prepare_smem(c, k_cg_fused_w_ring<U, S, MINB>, smem, &prepared));
   CU(c, tl_launch(c, k_cg_fused_w_ring<U, S, MINB>, c->fused_grid, TL_FUSED_THREADS, smem, P));
@@ -1352,14 +1362,18 @@ static int launch_cg_a_tma(tl_ctx *c, const CgAParams &A) {
   return TL_OK;
 }
 
-template <bool U>
+template <int U>
 static int launch_cg_a(tl_ctx *c) {
   const CgAParams P = cg_a_params(c);
   if (c->a_tma) {
-    if (c->a_tma == 3) TRY((launch_cg_a_tma<U, 3, 2>(c, P)));
-    else TRY((launch_cg_a_tma<U, 4, 2>(c, P)));
-    CHECK_LAUNCH(c);
-    return TL_OK;
+    if constexpr (U == TL_U_LAZY) {
+      return tl_fail(c, TL_ERR_STATE, "internal: the TMA flavour has no lazy-u mode");
+    } else {
+      if (c->a_tma == 3) TRY((launch_cg_a_tma<U != TL_U_NONE, 3, 2>(c, P)));
+      else TRY((launch_cg_a_tma<U != TL_U_NONE, 4, 2>(c, P)));
+      CHECK_LAUNCH(c);
+      return TL_OK;
+    }
   }
   switch (c->ring_eff) {
     case 3: TRY((launch_ring<U, 3, 3>(c, P))); break;
@@ -1450,7 +1464,8 @@ static int enqueue_cg_iteration(tl_ctx *c) {
     TRY(pull_halo(c, TL_P, 1));
     TRY(pull_halo(c, B_P1, 1));
   }
-  TRY(launch_cg_a<true>(c));
+  if (cg_u_mode(c) == TL_U_LAZY) TRY(launch_cg_a<TL_U_LAZY>(c));
+  else TRY(launch_cg_a<TL_U_EVERY>(c));
   if (legacy) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
   TRY(launch_cg_b(c));
   if (legacy) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
@@ -1582,8 +1597,9 @@ static int cg_phase(tl_ctx *c, SolveState *fin) {
 static int cg_flush(tl_ctx *c, int iters_done, bool update_u) {
   CgAParams P = cg_a_params(c);
   P.t = c->pw_tiling;
-  if (update_u) k_cg_flush<true><<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
-  else k_cg_flush<false><<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
+  if (!update_u) k_cg_flush<TL_U_NONE><<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
+  else if (cg_u_mode(c) == TL_U_LAZY) k_cg_flush<TL_U_LAZY><<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
+  else k_cg_flush<TL_U_EVERY><<<c->pw_grid, TL_FUSED_THREADS, 0, c->stream>>>(P);
   c->launches++;
   CHECK_LAUNCH(c);
   c->p_cur = iters_done & 1;
@@ -1991,7 +2007,7 @@ static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k, bool pair
   const bool legacy = legacy_comm(c);
   if (pairs) {
     const int npairs = inner_steps / 2;
-    TRY(launch_cg_a<false>(c));
+    TRY(launch_cg_a<TL_U_NONE>(c));
     PpcgUrParams U = ppcg_ur_params(c);
     const int rin0 = ppcg_pair_rin(0, npairs);       // r goes where the first pair reads it
     if (c->nranks > 1) {                             // tiles: sd two cells / r one cell deep into the eight surrounding tiles
@@ -2008,7 +2024,7 @@ static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k, bool pair
   }
   if (depth_k > 1) {
     // matrix-powers groups: one tile exchange per depth_k inner steps (PpcgDkParams)
-    TRY(launch_cg_a<false>(c));
+    TRY(launch_cg_a<TL_U_NONE>(c));
     TRY(prepare_ur_sd(c));
     CU(c, tl_launch(c, k_ppcg_ur_sd, c->pw_grid, TL_FUSED_THREADS, 0, ppcg_ur_params_dk(c, inner_steps, depth_k)));
     for (int pp = 0; pp < inner_steps; pp++) TRY(launch_ppcg_dk(c));
@@ -2020,7 +2036,7 @@ static int enqueue_ppcg_outer(tl_ctx *c, int inner_steps, int depth_k, bool pair
     TRY(pull_halo(c, TL_P, 1));
     TRY(pull_halo(c, B_P1, 1));
   }
-  TRY(launch_cg_a<false>(c));
+  TRY(launch_cg_a<TL_U_NONE>(c));
   if (legacy) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
   TRY(prepare_ur_sd(c));
   CU(c, tl_launch(c, k_ppcg_ur_sd, c->pw_grid, TL_FUSED_THREADS, 0, ppcg_ur_params(c)));
@@ -2257,12 +2273,12 @@ extern "C" int tl_jacobi_solve(tl_ctx *c, int coef, double rx, double ry, double
 // ---------------------------------------------------------------------------------------
 // measurement helper
 // ---------------------------------------------------------------------------------------
-__global__ void k_state_for_timing(SolveState *st, double *hist_rr, double *hist_pw, double *cha, double *chb, int n) {
+__global__ void k_state_for_timing(SolveState *st, double *hist_rr, double *hist_pw, double *cha, double *chb, int n, int iter) {
   StopCfg cfg{INT_MAX, TL_CONV_ABS, INT_MAX, 0, 0.0, 0.0};
   st->cfg = cfg;
-  st->iter = 2;
+  st->iter = iter;
   st->red_rr = 1.0; st->red_pw = 1e300;
-  hist_rr[1] = 1.0; hist_rr[2] = 1.0; hist_pw[2] = 1e300; hist_pw[3] = 1e300;
+  for (int i = 0; i < 5; i++) { hist_rr[i] = 1.0; hist_pw[i] = 1e300; }
   st->theta = 1.0; st->eps_cheby = 0.0; st->cheby_step = 1; st->cheby_pairs = 0; st->cheby_est = INT_MAX;
   st->cheby_tt0 = 1; st->cheby_max_tt = INT_MAX; st->inner_steps = INT_MAX; st->inner_pp = 0; st->counter = 0u;
   for (int i = 0; i < n; i++) { cha[i] = 0.5; chb[i] = 1e-3; }
@@ -2274,11 +2290,16 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
   CU(c, cudaSetDevice(c->device));
   const std::string k(kernel);
   reps = std::min(reps, c->max_iters - 4);
-  k_state_for_timing<<<1, 1, 0, c->stream>>>(c->st, c->hist_rr, c->hist_pw, c->ch_alphas, c->ch_betas, c->max_iters);
+  const int t_iter = (k == "cg_fused_w_odd") ? 3 : 2;
+  k_state_for_timing<<<1, 1, 0, c->stream>>>(c->st, c->hist_rr, c->hist_pw, c->ch_alphas, c->ch_betas, c->max_iters, t_iter);
   CHECK_LAUNCH(c);
   auto launch = [&]() -> int {
-    if (k == "cg_fused_w") TRY(launch_cg_a<true>(c));
-    else if (k == "cg_fused_w_nou") TRY(launch_cg_a<false>(c));
+    if (k == "cg_fused_w" || k == "cg_fused_w_odd") {
+      // the kernel of the CG loop; lazy-u mode: iteration 2 applies both pending u updates, "_odd" (iteration 3) none
+      if (cg_u_mode(c) == TL_U_LAZY) TRY(launch_cg_a<TL_U_LAZY>(c));
+      else TRY(launch_cg_a<TL_U_EVERY>(c));
+    }
+    else if (k == "cg_fused_w_nou") TRY(launch_cg_a<TL_U_NONE>(c));
     else if (k == "cg_fused_r") TRY(launch_cg_b(c));
     else if (k == "cheby_fused") TRY(launch_cheby<false>(c));
     else if (k == "cheby_pair") { TRY(enqueue_cheby_pair(c)); c->launches--; }
@@ -2295,7 +2316,7 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
   if (k == "ppcg_pair") reps = std::min(reps, (c->max_iters - 16) / 2);
   if (k == "cheby_pair") { reps = std::min(reps, (c->max_iters - 16) / 2); k_state_set_step<<<1, 1, 0, c->stream>>>(c->st, 2); }
   if (k == "cg_fused_r") {  // B advances the iteration counter: rewind it
-    k_state_for_timing<<<1, 1, 0, c->stream>>>(c->st, c->hist_rr, c->hist_pw, c->ch_alphas, c->ch_betas, c->max_iters);
+    k_state_for_timing<<<1, 1, 0, c->stream>>>(c->st, c->hist_rr, c->hist_pw, c->ch_alphas, c->ch_betas, c->max_iters, t_iter);
   }
   CU(c, cudaEventRecord(c->ev_start, c->stream));
   for (int i = 0; i < reps; i++) TRY(launch());

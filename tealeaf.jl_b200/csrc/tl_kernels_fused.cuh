@@ -123,7 +123,8 @@ __device__ __forceinline__ void tl_reflect_edges(double *f, const Geo &g, const 
 // then  w = A p , pw = sum(p.w)  (CG.w! CG.jl:82-90).  p is ping-ponged between p0/p1 because
 // neighbouring warps still read the old p.  UPDATE_U = false is the PPCG outer variant (u is
 // advanced by k_ppcg_ur_sd instead).
-// HBM traffic per cell: read r, p, u, kx, ky; write p, u, w  = 64 B (48 B without u).
+// HBM traffic per cell: read r, p, u, kx, ky; write p, u, w  = 64 B (48 B without u; TL_U_LAZY, the default of the CG
+// loop, touches u every second launch only: 72 / 48 B, see tl_kernels_ring.cuh).
 // ------------------------------------------------------------------------------------------
 struct CgAParams {
   Geo g; Tiling t;
@@ -223,17 +224,22 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBPar
 // (u += alpha p ; p = beta p + r) including the depth-1 halo write-through, so that memory
 // holds the reference's post-iteration state.  Pointwise.
 // ------------------------------------------------------------------------------------------
-template <bool UPDATE_U>
+// UM: how the loop's kernel A advanced u (TL_U_NONE / TL_U_EVERY / TL_U_LAZY, tl_kernels_ring.cuh -- 0 / 1 / 2);
+// after a TL_U_LAZY loop one or two updates are pending, the older p still sits in the other ping-pong buffer.
+template <int UM>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_flush(const CgAParams P) {
   SolveState *st = P.st;
   const int it = st->iter;
   if (it == st->cfg.first_it) return;
   const double rr_cur = st->red_rr, rr_prev = P.hist_rr[it - 1];
   const double beta = rr_cur / rr_prev, alpha = rr_prev / P.hist_pw[it];
+  const bool two = (UM == 2) && ((it - st->cfg.first_it) & 1) == 0;
+  const double alpha2 = two ? P.hist_rr[it - 2] / P.hist_pw[it - 1] : 0.0;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_rr[it] = rr_cur;
   // pointwise, so done IN PLACE in the buffer kernel A of iteration `it` wrote: the current p
   // stays buffer (it & 1) and a following phase (Chebyshev / PPCG) starts from it.
   double *pin = (it & 1) ? P.p1 : P.p0;
+  const double *pold = (it & 1) ? P.p0 : P.p1;
   double *pout = pin;
   const Geo g = P.g;
   const bool physL = g.phys & TL_PHYS_LEFT, physR = g.phys & TL_PHYS_RIGHT;
@@ -250,11 +256,16 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_flush(const CgAParam
       const double pn = beta * pv + P.r[o];
       pout[o] = pn;
       double un = 0.0;
-      if (UPDATE_U) { un = P.u[o] + alpha * pv; P.u[o] = un; }
-      if (physL && i == 0) { pout[o - 1] = pn; if (UPDATE_U) P.u[o - 1] = un; }
-      if (physR && i == g.nx - 1) { pout[o + 1] = pn; if (UPDATE_U) P.u[o + 1] = un; }
-      if (physB && j == 0) { pout[o - g.pitch] = pn; if (UPDATE_U) P.u[o - g.pitch] = un; }
-      if (physT && j == g.ny - 1) { pout[o + g.pitch] = pn; if (UPDATE_U) P.u[o + g.pitch] = un; }
+      if (UM != 0) {
+        un = P.u[o];
+        if (two) un = un + alpha2 * pold[o];
+        un = un + alpha * pv;
+        P.u[o] = un;
+      }
+      if (physL && i == 0) { pout[o - 1] = pn; if (UM != 0) P.u[o - 1] = un; }
+      if (physR && i == g.nx - 1) { pout[o + 1] = pn; if (UM != 0) P.u[o + 1] = un; }
+      if (physB && j == 0) { pout[o - g.pitch] = pn; if (UM != 0) P.u[o - g.pitch] = un; }
+      if (physT && j == g.ny - 1) { pout[o + g.pitch] = pn; if (UM != 0) P.u[o + g.pitch] = un; }
     }
   }
 }

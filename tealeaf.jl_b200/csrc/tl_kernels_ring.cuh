@@ -47,16 +47,38 @@ struct CgAIter {
   int it;
   bool first;
   double beta, alpha_prev;
+  bool upd2;            // TL_U_LAZY: this launch applies the two pending u updates (else none)
+  double alpha_prev2;   // alpha of iteration it-2
 };
+
+// How kernel A advances u (template parameter UM):
+//   TL_U_NONE   never (PPCG outer: k_ppcg_ur_sd does it)
+//   TL_U_EVERY  every launch: u += alpha(it-1) p(it-1)                                    (64 B per cell)
+//   TL_U_LAZY   every second launch: u = (u + alpha(it-2) p(it-2)) + alpha(it-1) p(it-1) -- p(it-2) still sits in the
+//               ping-pong buffer this launch is about to overwrite, so it costs one more read of 8 B, and the launches
+//               in between neither read nor write u: 72 / 48 B per cell, 60 on average.  Same operations in the
+//               same order as two single updates (CG.jl:95), hence the same bits.
+#define TL_U_NONE 0
+#define TL_U_EVERY 1
+#define TL_U_LAZY 2
+#define TL_CGA_FIELDS(UM) ((UM) == TL_U_LAZY ? 6 : TL_RING_FIELDS)
+#define TL_CGA_STAGE_BYTES(UM) (TL_CGA_FIELDS(UM) * 512 + 64)
+// pending u updates after `off` executed iterations of a TL_U_LAZY phase (off >= 1)
+__host__ __device__ inline int tl_cg_lazy_pending(int off) { return (off & 1) ? 1 : 2; }
 
 // The rows of one work item (8 warp tasks) of kernel A.  COH = true (persistent kernel: r, p, u change
 // inside the launch) keeps the prologue loads coherent; the ring loads are cp.async (L2) either way.
-template <bool UPDATE_U, int S, bool COH>
+template <int UM, int S, bool COH>
 __device__ __forceinline__ void tl_cg_a_item(const CgAParams &P, const CgAIter &I, int blk, unsigned char *ring_raw,
                                              double &acc0) {
+  constexpr unsigned STAGE = TL_CGA_STAGE_BYTES(UM);
+  constexpr unsigned NF = TL_CGA_FIELDS(UM);
   const int it = I.it;
   const bool first = I.first;
   const double beta = I.beta, alpha_prev = I.alpha_prev;
+  const bool upd2 = (UM == TL_U_LAZY) && I.upd2;          // uniform over the launch
+  const bool upd = (UM == TL_U_EVERY) || upd2;
+  const double alpha_prev2 = I.alpha_prev2;
   const double *__restrict__ pin = (it & 1) ? P.p1 : P.p0;
   double *__restrict__ pout = (it & 1) ? P.p0 : P.p1;
   const double *__restrict__ r = P.r;
@@ -78,11 +100,11 @@ __device__ __forceinline__ void tl_cg_a_item(const CgAParams &P, const CgAIter &
   auto comb = [&](double rv, double pv) { return first ? pv : beta * pv + rv; };
   auto comb2 = [&](double2 rv, double2 pv) { return make_double2(comb(rv.x, pv.x), comb(rv.y, pv.y)); };
   // this warp's ring; slot layout: [field 0..4][lane] double2, then 8 edge doubles
-  const unsigned ring = tl_smem_u32(ring_raw) + (threadIdx.x >> 5) * (S * TL_RING_STAGE_BYTES);
+  const unsigned ring = tl_smem_u32(ring_raw) + (threadIdx.x >> 5) * (S * STAGE);
   const unsigned lane_off = m.lane * 16;
-  const unsigned edge_off = TL_RING_FIELDS * 512 + (m.lane == 0 ? 0 : 24);   // lane 0: 3 doubles, lane 31: 3 doubles
+  const unsigned edge_off = NF * 512 + (m.lane == 0 ? 0 : 24);   // lane 0: 3 doubles, lane 31: 3 doubles
   auto issue = [&](int j, int stage) {
-    const unsigned base = ring + stage * TL_RING_STAGE_BYTES;
+    const unsigned base = ring + stage * STAGE;
     const int jn = (j + 1 >= g.ny && physT) ? g.ny - 1 : j + 1;
     const long on = (long)jn * pitch + m.i0, oc = (long)j * pitch + m.i0;
     if (m.ld_ok) {
@@ -91,7 +113,8 @@ __device__ __forceinline__ void tl_cg_a_item(const CgAParams &P, const CgAIter &
       tl_cp16_hint(base + 2 * 512 + lane_off, ky + oc + pitch, pol_stream);
       tl_cp16_hint(base + 3 * 512 + lane_off, kx + oc, pol_stream);
     }
-    if (UPDATE_U && m.acta) tl_cp16_hint(base + 4 * 512 + lane_off, u + oc, pol_stream);
+    if (upd && m.acta) tl_cp16_hint(base + 4 * 512 + lane_off, u + oc, pol_stream);
+    if (upd2 && m.acta) tl_cp16_hint(base + 5 * 512 + lane_off, pout + oc, pol_stream);   // p(it-2), before it is overwritten
     if (m.has_edge) {
       const long oe = (long)jn * pitch + m.ecol;
       tl_cp8(base + edge_off + 0, r + oe);
@@ -126,12 +149,17 @@ __device__ __forceinline__ void tl_cg_a_item(const CgAParams &P, const CgAIter &
     if (j + S - 1 < m.j1) issue(j + S - 1, fill);
     tl_cp_commit();
     tl_cp_wait<S - 1>();
-    const unsigned base = ring + stage * TL_RING_STAGE_BYTES;
+    const unsigned base = ring + stage * STAGE;
     const double2 c_r = m.ld_ok ? tl_lds2(base + 0 * 512 + lane_off) : z2;
     const double2 c_p = m.ld_ok ? tl_lds2(base + 1 * 512 + lane_off) : z2;
     const double2 c_ky = m.ld_ok ? tl_lds2(base + 2 * 512 + lane_off) : z2;
     const double2 c_kx = m.ld_ok ? tl_lds2(base + 3 * 512 + lane_off) : z2;
-    const double2 c_u = (UPDATE_U && m.acta) ? tl_lds2(base + 4 * 512 + lane_off) : z2;
+    double2 c_u = (upd && m.acta) ? tl_lds2(base + 4 * 512 + lane_off) : z2;
+    if (UM == TL_U_LAZY && upd2 && m.acta) {
+      const double2 c_po = tl_lds2(base + 5 * 512 + lane_off);
+      c_u.x = c_u.x + alpha_prev2 * c_po.x;
+      c_u.y = c_u.y + alpha_prev2 * c_po.y;
+    }
     const double c_re = m.has_edge ? tl_lds1(base + edge_off + 0) : 0.0;
     const double c_pe = m.has_edge ? tl_lds1(base + edge_off + 8) : 0.0;
     const double c_kxe = (m.lane == 31 && m.has_edge) ? tl_lds1(base + edge_off + 16) : 0.0;
@@ -155,29 +183,29 @@ __device__ __forceinline__ void tl_cg_a_item(const CgAParams &P, const CgAIter &
                       (kxr * Rb + c_kx.y * Lb) - (c_ky.y * Xn.y + kyc.y * Xm.y);
     const long oc = (long)j * pitch + m.i0;
     double2 un = z2;
-    if (UPDATE_U) un = make_double2(c_u.x + alpha_prev * pc.x, c_u.y + alpha_prev * pc.y);
+    if (UM != TL_U_NONE) un = make_double2(c_u.x + alpha_prev * pc.x, c_u.y + alpha_prev * pc.y);
     if (m.actb) {
       tl_st2_hint(w + oc, make_double2(wa, wb), pol_keep);
       tl_st2_hint(pout + oc, Xc, pol_stream);
-      if (UPDATE_U) tl_st2_hint(u + oc, un, pol_stream);
+      if (upd) tl_st2_hint(u + oc, un, pol_stream);
       acc0 += wa * Xc.x;
       acc0 += wb * Xc.y;
     } else if (m.acta) {
       w[oc] = wa; pout[oc] = Xc.x;
-      if (UPDATE_U) u[oc] = un.x;
+      if (upd) u[oc] = un.x;
       acc0 += wa * Xc.x;
     }
     // haloupdate!(.., [:u,:p]) CG.jl:22: reflective sides as a write-through, tile-internal
     // sides as a push of p into the neighbour's halo (u's internal halos are filled after the loop)
     tl_reflect_edges(pout, g, m, j, oc, Xc);
-    if (UPDATE_U) tl_reflect_edges(u, g, m, j, oc, un);
+    if (upd) tl_reflect_edges(u, g, m, j, oc, un);
     if (tiled) tl_push_edges(push, g, m, j, Xc);
     Xm = Xc; Xc = Xn; XcE = XnE; pc = c_p; kyc = c_ky;
   }
   tl_cp_wait<0>();
 }
 
-template <bool UPDATE_U, int S, int MINB>
+template <int UM, int S, int MINB>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(const CgAParams P) {
   tl_pdl_entry();
   extern __shared__ __align__(128) unsigned char ring_raw[];
@@ -192,14 +220,22 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
   I.it = it;
   I.first = (it == st->cfg.first_it);
   I.beta = 0.0; I.alpha_prev = 0.0;
+  I.upd2 = false; I.alpha_prev2 = 0.0;
   if (!I.first) {
     const double rr_prev = P.hist_rr[it - 1];
     I.beta = rr_cur / rr_prev;
     I.alpha_prev = rr_prev / P.hist_pw[it];
+    if (UM == TL_U_LAZY) {
+      const int off = it - st->cfg.first_it;      // iterations executed so far in this phase
+      if (off >= 2 && tl_cg_lazy_pending(off) == 2) {
+        I.upd2 = true;
+        I.alpha_prev2 = P.hist_rr[it - 2] / P.hist_pw[it - 1];
+      }
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_rr[it] = rr_cur;
   double acc[1] = {0.0};
-  tl_cg_a_item<UPDATE_U, S, false>(P, I, blockIdx.x, ring_raw, acc[0]);
+  tl_cg_a_item<UM, S, false>(P, I, blockIdx.x, ring_raw, acc[0]);
   if (tl_kernel_tail(acc, true, st, P.partials, P.cd, sm, TL_T_PW)) {
     st->red_pw_local = acc[0];
     if ((P.single || P.cd != nullptr) && !tl_is_deferred(P.cd)) st->red_pw = acc[0];

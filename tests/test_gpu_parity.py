@@ -396,6 +396,42 @@ def test_kernel_a_tma_is_bit_identical(nx, ny, solver, over, slots):
     np.testing.assert_array_equal(a[4], b[4])
 
 
+LAZY_U_CASES = [(200, 120, "cg", {}, {}), (257, 19, "cg", {}, {}), (1, 40, "cg", {}, {}), (64, 5, "cg", {}, {"use_graph": 0}),
+                (96, 80, "cg", {"maxiters": 1}, {}), (96, 80, "cg", {"maxiters": 2}, {}), (96, 80, "cg", {"maxiters": 3}, {}),
+                (96, 80, "cg", {"maxiters": 4}, {"graph_iters": 3}), (96, 80, "cg", {"maxiters": 9}, {"graph_iters": 1}),
+                (700, 523, "cg", {"maxiters": 400}, {}), (700, 523, "cg", {"maxiters": 401}, {"ring_stages": 4}),
+                (300, 260, "cg", {"maxiters": 77}, {"ring_stages": 6}), (2048, 1536, "cg", {"maxiters": 121}, {}),
+                (129, 70, "cg", {"halodepth": 3}, {}), (128, 96, "cheby", {}, {}), (130, 97, "cheby", {"presteps": 31}, {}),
+                (96, 160, "ppcg", {"ppcginnersteps": 6}, {}), (96, 161, "ppcg", {"ppcginnersteps": 5, "presteps": 29}, {})]
+
+
+@pytest.mark.parametrize("nx,ny,solver,over,opts", LAZY_U_CASES,
+                         ids=[f"{c[2]}-{c[0]}x{c[1]}-" + "-".join(f"{k}{v}" for k, v in {**c[3], **c[4]}.items()) for c in LAZY_U_CASES])
+def test_lazy_u_update_is_bit_identical(nx, ny, solver, over, opts):
+    """Option cg_lazy_u (default on): kernel A of the CG loop advances u every second launch with both pending updates,
+    u = (u + alpha(it-2) p(it-2)) + alpha(it-1) p(it-1), and the flush applies the one or two that remain -- the same
+    operations in the same order as an update per iteration (CG.jl:95): every field and scalar has the same bits, for odd
+    and even iteration counts, odd graph lengths, every ring depth, and across a switch to Chebyshev / PPCG."""
+    outs = []
+    for lazy in (0, 1):
+        s = classic_settings(nx, ny=ny, steps=2, solver=solver, **over)
+        chunk, geom = tl.initialiseapp(s, backend=_device())
+        chunk.set_option("cg_lazy_u", lazy)
+        for k, v in opts.items():
+            chunk.set_option(k, v)
+        assert chunk.get_option("cg_u_mode") == (2 if lazy else 1)
+        recs, final = tl.diffuse(chunk, s, geom)
+        outs.append(([(r["iters"], r["cg_iters"], r["error"]) for r in recs], final["temp"],
+                     {f: chunk.get_field(f) for f in ("u", "energy", "p", "r", "w", "sd")}, chunk.cgalpha.copy(), chunk.cgbeta.copy()))
+        chunk.close()
+    a, b = outs
+    assert a[:2] == b[:2], (a[:2], b[:2])
+    for f in a[2]:
+        np.testing.assert_array_equal(a[2][f], b[2][f], err_msg=f)
+    np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(a[4], b[4])
+
+
 @pytest.mark.parametrize("depth", [6, 8])
 @pytest.mark.parametrize("nx,ny", [(200, 120), (257, 19), (1, 40), (700, 523)])
 def test_kernel_b_ring_is_bit_identical(nx, ny, depth):

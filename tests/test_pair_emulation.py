@@ -48,3 +48,12 @@ def test_tiled_ppcg_pair_design_halo_depths_are_necessary():
     assert not emulate_ppcg_pair_tiled.run(130, 12, 2, 2, 3, ds=1)
     assert not emulate_ppcg_pair_tiled.run(130, 12, 2, 2, 3, dr=0)
     assert not emulate_ppcg_pair_tiled.run(130, 12, 2, 2, 3, dk=1)
+
+
+@pytest.mark.parametrize("first", [0, 1, 30])
+def test_lazy_u_schedule_of_cg_kernel_a(first):
+    """TL_U_LAZY: u advanced every second launch with both pending updates + the flush = an update per iteration, bit for bit,
+    whatever the number of iterations and the parity of the phase's first iteration."""
+    import emulate_lazy_u
+    for n in range(0, 12):
+        assert emulate_lazy_u.run(n, first), n

@@ -212,3 +212,23 @@ def test_split_exchange_is_bit_identical(grid, solver, nx, ny, over):
     for f in fields:
         np.testing.assert_array_equal(base[2][f][hd:-hd, hd:-hd], split[2][f][hd:-hd, hd:-hd], err_msg=f)
     check_against_oracle(split, run_oracle(solver, nx, ny, steps=2, over=over), solver, hd=hd)
+
+
+# ---- lazy u update of CG kernel A (option cg_lazy_u, default on) on tiles ------------------------------------------
+LAZY_TILED_CASES = [((2, 2), "cg", 200, 150, {}), ((1, 4), "cg", 96, 256, {"maxiters": 41}), ((3, 2), "cg", 131, 77, {"maxiters": 40}),
+                    ((2, 2), "cheby", 129, 140, {}), ((2, 2), "ppcg", 131, 150, {"ppcginnersteps": 5})]
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("grid,solver,nx,ny,over", LAZY_TILED_CASES, ids=[f"{g[0]}x{g[1]}-{s}-{nx}x{ny}" for g, s, nx, ny, o in LAZY_TILED_CASES])
+def test_lazy_u_update_is_bit_identical_on_tiles(grid, solver, nx, ny, over):
+    """u's tile-internal halos are filled after the loop (pull), so the lazy update needs nothing new on tiles: same bits."""
+    fields = ("u", "energy", "p", "r", "w")
+    base = run_tiled(grid, solver, nx, ny, steps=2, over=over, options={"cg_lazy_u": 0}, fields=fields)
+    lazy = run_tiled(grid, solver, nx, ny, steps=2, over=over, options={"cg_lazy_u": 1}, fields=fields)
+    key = lambda recs: [(r["iters"], r["cg_iters"], r["cheby_iters"], r["inner_total"], r["error"]) for r in recs]
+    assert key(base[0]) == key(lazy[0])
+    assert base[1] == lazy[1]
+    for f in fields:
+        np.testing.assert_array_equal(base[2][f], lazy[2][f], err_msg=f)
+    check_against_oracle(lazy, run_oracle(solver, nx, ny, steps=2, over=over), solver)
