@@ -106,6 +106,10 @@ int tl_abi_version(void);
  *   a_tma                       kernel A's row ring filled by TMA (cp.async.bulk.tensor + mbarriers): 0 off (default: measured,
  *                               not faster), 3 / 4 ring slots
  *   cg_persist                  1: the CG loop of a single tile as ONE persistent cooperative kernel
+ *   cg_lazy_u                   CG loop: u advanced every second iteration with both pending updates, in the same order as one
+ *                               update per iteration (bit-identical; 84 instead of 88 bytes per cell-iteration; default 1; needs an
+ *                               even graph_iters and the cp.async flavour of kernel A, else one update per iteration)
+ *   cg_lazy_heavy_ctas          the u-updating launch of that loop at ring depth 3: 2 (default) or 3 CTAs per SM
  *   cheby_pair, ppcg_pair       two Chebyshev iterations / PPCG inner steps per pass (temporal blocking; default 1)
  *   pair_tiled                  the pair kernels also on tiles: depth-2 halos, one exchange per two iterations (default 1)
  *   pair_rows                   rows per warp task of the pair kernels (32)
@@ -126,7 +130,8 @@ int tl_abi_version(void);
 int tl_set_option(tl_ctx *ctx, const char *name, double value);
 /* Read-back of any option above, and of derived quantities: ring_stages_effective (the ring depth in use),
  * rows_per_chunk / pw_rows_per_chunk / pair_rows_per_chunk and fused_grid / pw_grid / pair_grid (how the tile
- * is cut into warp tasks and CTAs), max_grid (the bound on a grid: the partials array), num_sms, last_cg_phase_ms
+ * is cut into warp tasks and CTAs), max_grid (the bound on a grid: the partials array), num_sms, cg_u_mode (1: u advanced every
+ * iteration, 2: every second one -- what cg_lazy_u resolves to), cg_a_blocks_per_sm (resident CTAs of kernel A), last_cg_phase_ms
  * (device time of the CG phase -- preamble, CG presteps, flush -- of the last Chebyshev / PPCG solve), prof_* (above).
  * On a tl_create_multi context: the maximum over the tiles. */
 int tl_get_option(tl_ctx *ctx, const char *name, double *value);

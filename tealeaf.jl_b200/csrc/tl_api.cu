@@ -137,7 +137,10 @@ struct tl_ctx {
   CUtensorMap tma_maps[TMA_NMAPS];
   bool tma_ready = false;
   int b_ring = 0;           // kernel B flavour: 0 = register batches of 4 rows; 6 / 8 = cp.async ring of that depth (4 / 3 CTAs per SM)
-  int cg_lazy_u = 0;        // 1: kernel A of the CG loop advances u every second launch (TL_U_LAZY, tl_kernels_ring.cuh)
+  int lazy_heavy_ctas = 2;  // CTAs per SM of the u-updating launch of the lazy loop at ring depth 3: 2 (116 registers, no spill, 164 KB
+                            // carve-out; measured 0.5-1 % faster per iteration at 4096^2) or 3 (80 registers, all-shared carve-out)
+  int cg_seq = 0;           // position of the next CG iteration in its chunk (lazy-u loop: which of the two kernels)
+  int cg_lazy_u = 1;        // 1: the CG loop advances u every second iteration with both pending updates (TL_U_LAZY, tl_kernels_ring.cuh)
   int cg_persist = 0;       // 1: the CG loop of a single tile runs as ONE persistent cooperative kernel (tl_kernels_persist.cuh)
   PersistSync *psync = nullptr;
   int comm_fused = 1;       // 1: halo pushes + mailbox allreduce inside the kernels; 0: halo-pull kernels + NCCL
@@ -378,7 +381,8 @@ extern "C" const char *tl_last_error(const tl_ctx *c) { return c ? c->err.c_str(
 // How the CG loop's kernel A advances u: every second launch (TL_U_LAZY, the default) unless a flavour without that
 // mode is selected (TMA ring, persistent kernel)
 static int cg_u_mode(const tl_ctx *c) {
-  return (c->cg_lazy_u && !c->a_tma && !(c->cg_persist && c->nranks == 1)) ? TL_U_LAZY : TL_U_EVERY;
+  // chunks of an even number of iterations: the two kernels of the lazy loop alternate by position in the chunk
+  return (c->cg_lazy_u && !c->a_tma && !(c->cg_persist && c->nranks == 1) && c->graph_iters % 2 == 0) ? TL_U_LAZY : TL_U_EVERY;
 }
 
 extern "C" int tl_set_option(tl_ctx *c, const char *name, double value);
@@ -557,6 +561,7 @@ extern "C" int tl_set_option(tl_ctx *c, const char *name, double value) {
   else if (n == "use_pdl") c->use_pdl = value != 0.0;   // programmatic dependent launch, released before the kernel tails (tl_pdl_trigger)
   else if (n == "cg_persist") c->cg_persist = value != 0.0;
   else if (n == "cg_lazy_u") c->cg_lazy_u = value != 0.0;
+  else if (n == "cg_lazy_heavy_ctas") c->lazy_heavy_ctas = value == 3.0 ? 3 : 2;
   else if (n == "a_tma") {   // 0 off; 1 / 4: TMA ring of 4 row slots; 3: of 3 row slots (two CTAs per SM either way)
     const int d = (int)value;
     if (d != 0 && d != 1 && d != 3 && d != 4) return tl_fail(c, TL_ERR_ARG, "a_tma must be 0, 1, 3 or 4");
@@ -614,6 +619,8 @@ __global__ void k_state_prof(SolveState *st, int on) {
 }
 
 // Read-back of an option or of a derived quantity (what the tests assert the measured code paths on).
+static int cg_a_occupancy(tl_ctx *c, int *out);
+
 extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
   if (TL_IS_MULTI(c)) {
     if (name && strncmp(name, "debug_", 6) == 0) return multi_min(c, value, [&](tl_ctx *t, double *o) { return tl_get_option(t, name, o); });
@@ -634,7 +641,14 @@ extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
   else if (n == "use_pdl") v = c->use_pdl;
   else if (n == "cg_persist") v = c->cg_persist;
   else if (n == "cg_lazy_u") v = c->cg_lazy_u;
+  else if (n == "cg_lazy_heavy_ctas") v = c->lazy_heavy_ctas;
   else if (n == "cg_u_mode") v = cg_u_mode(c);
+  else if (n == "cg_a_blocks_per_sm") {
+    int occ = 0;
+    CU(c, cudaSetDevice(c->device));
+    TRY(cg_a_occupancy(c, &occ));
+    v = occ;
+  }
   else if (n == "a_tma") v = c->a_tma;
   else if (n == "balanced_tiling") v = c->balanced_tiling;
   else if (n == "cheby_pair") v = c->cheby_pair;
@@ -1299,6 +1313,7 @@ static CgAParams cg_a_params(tl_ctx *c) {
   P.single = c->nranks == 1;
   P.hint_keep = c->hint_keep; P.hint_stream = c->hint_stream;
   P.cd = comm_dev(c); P.push_p0 = push_for(c, TL_P); P.push_p1 = push_for(c, B_P1);
+  P.lazy_role = 0;
   return P;
 }
 static CgBParams cg_b_params(tl_ctx *c) {
@@ -1363,8 +1378,9 @@ static int launch_cg_a_tma(tl_ctx *c, const CgAParams &A) {
 }
 
 template <int U>
-static int launch_cg_a(tl_ctx *c) {
-  const CgAParams P = cg_a_params(c);
+static int launch_cg_a(tl_ctx *c, int lazy_role = 0) {
+  CgAParams P = cg_a_params(c);
+  P.lazy_role = lazy_role;
   if (c->a_tma) {
     if constexpr (U == TL_U_LAZY) {
       return tl_fail(c, TL_ERR_STATE, "internal: the TMA flavour has no lazy-u mode");
@@ -1376,13 +1392,39 @@ static int launch_cg_a(tl_ctx *c) {
     }
   }
   switch (c->ring_eff) {
-    case 3: TRY((launch_ring<U, 3, 3>(c, P))); break;
+    case 3:
+      if constexpr (U == TL_U_LAZY) {
+        if (c->lazy_heavy_ctas == 2) { TRY((launch_ring<U, 3, 2>(c, P))); break; }
+      }
+      TRY((launch_ring<U, 3, 3>(c, P)));
+      break;
     case 4: TRY((launch_ring<U, 4, 2>(c, P))); break;
     case 6: TRY((launch_ring<U, 6, 1>(c, P))); break;
     default: return tl_fail(c, TL_ERR_STATE, "internal: ring depth %d", c->ring_eff);
   }
   CHECK_LAUNCH(c);
   return TL_OK;
+}
+
+// resident CTAs per SM of the CG loop's kernel A as configured (read-back "cg_a_blocks_per_sm")
+template <int U, int S, int MINB>
+static int ring_occupancy(tl_ctx *c, int *out) {
+  const int smem = (TL_FUSED_THREADS / 32) * S * TL_CGA_STAGE_BYTES(U);
+  static std::atomic<unsigned long long> prepared{0};
+  TRY(tl_prepare_smem(c, k_cg_fused_w_ring<U, S, MINB>, smem, &prepared));
+  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k_cg_fused_w_ring<U, S, MINB>, TL_FUSED_THREADS, smem));
+  return TL_OK;
+}
+static int cg_a_occupancy(tl_ctx *c, int *out) {
+  const bool lazy = cg_u_mode(c) == TL_U_LAZY;
+  switch (c->ring_eff) {
+    case 3:
+      if (lazy) return c->lazy_heavy_ctas == 2 ? ring_occupancy<TL_U_LAZY, 3, 2>(c, out) : ring_occupancy<TL_U_LAZY, 3, 3>(c, out);
+      return ring_occupancy<TL_U_EVERY, 3, 3>(c, out);
+    case 4: return lazy ? ring_occupancy<TL_U_LAZY, 4, 2>(c, out) : ring_occupancy<TL_U_EVERY, 4, 2>(c, out);
+    case 6: return lazy ? ring_occupancy<TL_U_LAZY, 6, 1>(c, out) : ring_occupancy<TL_U_EVERY, 6, 1>(c, out);
+  }
+  return tl_fail(c, TL_ERR_STATE, "internal: ring depth %d", c->ring_eff);
 }
 
 template <bool FIRST, int S, int MINB>
@@ -1464,8 +1506,12 @@ static int enqueue_cg_iteration(tl_ctx *c) {
     TRY(pull_halo(c, TL_P, 1));
     TRY(pull_halo(c, B_P1, 1));
   }
-  if (cg_u_mode(c) == TL_U_LAZY) TRY(launch_cg_a<TL_U_LAZY>(c));
-  else TRY(launch_cg_a<TL_U_EVERY>(c));
+  if (cg_u_mode(c) == TL_U_LAZY) {   // even position in the chunk = even iteration of the phase: both pending u updates
+    if ((c->cg_seq++ & 1) == 0) TRY(launch_cg_a<TL_U_LAZY>(c, 2));
+    else TRY(launch_cg_a<TL_U_NONE>(c, 1));
+  } else {
+    TRY(launch_cg_a<TL_U_EVERY>(c));
+  }
   if (legacy) TRY(allreduce2(c, &c->st->red_pw_local, &c->st->red_pw, 1));
   TRY(launch_cg_b(c));
   if (legacy) TRY(allreduce2(c, &c->st->red_rr_local, &c->st->red_rr, 1));
@@ -1479,6 +1525,7 @@ static int build_graph(tl_ctx *c, cudaGraphExec_t *exec, int reps, F enqueue_one
   CU(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   int rc = TL_OK;
   const long long saved = c->launches;
+  c->cg_seq = 0;
   for (int i = 0; i < reps && rc == TL_OK; i++) rc = enqueue_one();
   if (rc == TL_OK) rc = xchg_finalize(c);   // the host reads the state after every chunk
   c->launches = saved;
@@ -1507,6 +1554,7 @@ static int run_chunks(tl_ctx *c, cudaGraphExec_t *exec, int *exec_iters, int chu
       CU(c, cudaGraphLaunch(*exec, c->stream));
       c->launches += launches_per_iter * chunk_iters + (xchg_deferred(c) ? 1 : 0);
     } else {
+      c->cg_seq = 0;
       for (int i = 0; i < chunk_iters; i++) TRY(enqueue_one());
       TRY(xchg_finalize(c));
     }
@@ -1514,11 +1562,12 @@ static int run_chunks(tl_ctx *c, cudaGraphExec_t *exec, int *exec_iters, int chu
     CU(c, cudaEventRecord(c->ev[k & 1], c->stream));
     if (k >= 1) {
       CU(c, cudaEventSynchronize(c->ev[(k - 1) & 1]));
-      if (stopped(c->h_st[(k - 1) & 1]) || c->h_st[(k - 1) & 1].comm_error) break;
+      if (stopped(c->h_st[(k - 1) & 1]) || c->h_st[(k - 1) & 1].comm_error || c->h_st[(k - 1) & 1].sched_error) break;
     }
   }
   CU(c, cudaStreamSynchronize(c->stream));
   *final_state = c->h_st[k & 1];
+  if (final_state->sched_error) return tl_fail(c, TL_ERR_STATE, "internal: a kernel of the lazy-u CG loop ran at an iteration of the wrong parity");
   if (final_state->comm_error)
     return tl_fail(c, TL_ERR_COMM, "tile exchange timed out: tile %d did not hear from tile %d in exchange %llu (a neighbour tile did not "
                    "reach the same kernel); state: iter %d, cheby_step %d, cheby_pairs %d, inner_pp %d", c->rank,
@@ -2296,8 +2345,9 @@ extern "C" int tl_time_kernel(tl_ctx *c, const char *kernel, int reps, double *a
   auto launch = [&]() -> int {
     if (k == "cg_fused_w" || k == "cg_fused_w_odd") {
       // the kernel of the CG loop; lazy-u mode: iteration 2 applies both pending u updates, "_odd" (iteration 3) none
-      if (cg_u_mode(c) == TL_U_LAZY) TRY(launch_cg_a<TL_U_LAZY>(c));
-      else TRY(launch_cg_a<TL_U_EVERY>(c));
+      if (cg_u_mode(c) != TL_U_LAZY) TRY(launch_cg_a<TL_U_EVERY>(c));
+      else if (t_iter == 2) TRY(launch_cg_a<TL_U_LAZY>(c, 2));
+      else TRY(launch_cg_a<TL_U_NONE>(c, 1));
     }
     else if (k == "cg_fused_w_nou") TRY(launch_cg_a<TL_U_NONE>(c));
     else if (k == "cg_fused_r") TRY(launch_cg_b(c));

@@ -73,7 +73,7 @@ struct SolveState {
   // raised when a neighbour did not answer within TL_XCHG_TIMEOUT_NS
   unsigned long long xseq;
   int comm_error;
-  int pad1;
+  int sched_error;      // internal assertion: a kernel of the lazy-u CG loop ran at an iteration of the wrong parity
   // tile_barrier(): an out-of-place all-tiles sum of `barrier_zero` (never written: stays 0.0) into
   // `barrier_out`, so that a rendezvous never accumulates into a slot somebody else uses
   double barrier_zero, barrier_out;

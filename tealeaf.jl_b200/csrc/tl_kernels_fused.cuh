@@ -136,6 +136,8 @@ struct CgAParams {
   int hint_keep, hint_stream;   // TL_HINT_*: L2 priority of r, w / of everything else
   const CommDev *cd;            // tiles exchange in the kernel tail (null: single tile or NCCL mode)
   Push push_p0, push_p1;        // halo targets of the p buffer being written
+  int lazy_role;                // 0: u is advanced by this kernel every launch or not at all; lazy CG loop (tl_kernels_ring.cuh):
+                                // 1 = a launch between two u updates (odd iterations), 2 = a launch that applies both (even)
 };
 
 // ------------------------------------------------------------------------------------------

@@ -47,23 +47,23 @@ struct CgAIter {
   int it;
   bool first;
   double beta, alpha_prev;
-  bool upd2;            // TL_U_LAZY: this launch applies the two pending u updates (else none)
-  double alpha_prev2;   // alpha of iteration it-2
+  double alpha_prev2;   // TL_U_LAZY: alpha of iteration it-2
 };
 
-// How kernel A advances u (template parameter UM):
-//   TL_U_NONE   never (PPCG outer: k_ppcg_ur_sd does it)
-//   TL_U_EVERY  every launch: u += alpha(it-1) p(it-1)                                    (64 B per cell)
-//   TL_U_LAZY   every second launch: u = (u + alpha(it-2) p(it-2)) + alpha(it-1) p(it-1) -- p(it-2) still sits in the
-//               ping-pong buffer this launch is about to overwrite, so it costs one more read of 8 B, and the launches
-//               in between neither read nor write u: 72 / 48 B per cell, 60 on average.  Same operations in the
-//               same order as two single updates (CG.jl:95), hence the same bits.
+// How a launch of kernel A advances u (template parameter UM):
+//   TL_U_NONE   not at all (PPCG outer: k_ppcg_ur_sd does it; the odd iterations of a lazy CG loop)        48 B per cell
+//   TL_U_EVERY  u += alpha(it-1) p(it-1)                                                                    64 B
+//   TL_U_LAZY   u = (u + alpha(it-2) p(it-2)) + alpha(it-1) p(it-1): p(it-2) still sits in the ping-pong
+//               buffer this launch is about to overwrite, so it costs one more read of 8 B                  72 B
+// A lazy CG loop (option cg_lazy_u) launches TL_U_LAZY on the even iterations of the phase and TL_U_NONE on the odd
+// ones: 60 B on average.  Same operations in the same order as an update per iteration (CG.jl:95), hence the same bits.
+// The host alternates the two kernels (chunks of an even number of iterations), each checks the parity it was given.
 #define TL_U_NONE 0
 #define TL_U_EVERY 1
 #define TL_U_LAZY 2
-#define TL_CGA_FIELDS(UM) ((UM) == TL_U_LAZY ? 6 : TL_RING_FIELDS)
+#define TL_CGA_FIELDS(UM) ((UM) == TL_U_LAZY ? 6 : (UM) == TL_U_EVERY ? 5 : 4)
 #define TL_CGA_STAGE_BYTES(UM) (TL_CGA_FIELDS(UM) * 512 + 64)
-// pending u updates after `off` executed iterations of a TL_U_LAZY phase (off >= 1)
+// pending u updates after `off` executed iterations of a lazy phase (off >= 1)
 __host__ __device__ inline int tl_cg_lazy_pending(int off) { return (off & 1) ? 1 : 2; }
 
 // The rows of one work item (8 warp tasks) of kernel A.  COH = true (persistent kernel: r, p, u change
@@ -73,11 +73,11 @@ __device__ __forceinline__ void tl_cg_a_item(const CgAParams &P, const CgAIter &
                                              double &acc0) {
   constexpr unsigned STAGE = TL_CGA_STAGE_BYTES(UM);
   constexpr unsigned NF = TL_CGA_FIELDS(UM);
+  constexpr bool upd2 = UM == TL_U_LAZY;
+  const bool upd = UM != TL_U_NONE && !(upd2 && I.first);   // the first iteration of a lazy phase has nothing pending
   const int it = I.it;
   const bool first = I.first;
   const double beta = I.beta, alpha_prev = I.alpha_prev;
-  const bool upd2 = (UM == TL_U_LAZY) && I.upd2;          // uniform over the launch
-  const bool upd = (UM == TL_U_EVERY) || upd2;
   const double alpha_prev2 = I.alpha_prev2;
   const double *__restrict__ pin = (it & 1) ? P.p1 : P.p0;
   double *__restrict__ pout = (it & 1) ? P.p0 : P.p1;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void tl_cg_a_item(const CgAParams &P, const CgAIter &
       tl_cp16_hint(base + 3 * 512 + lane_off, kx + oc, pol_stream);
     }
     if (upd && m.acta) tl_cp16_hint(base + 4 * 512 + lane_off, u + oc, pol_stream);
-    if (upd2 && m.acta) tl_cp16_hint(base + 5 * 512 + lane_off, pout + oc, pol_stream);   // p(it-2), before it is overwritten
+    if (upd2 && upd && m.acta) tl_cp16_hint(base + 5 * 512 + lane_off, pout + oc, pol_stream);   // p(it-2), before it is overwritten
     if (m.has_edge) {
       const long oe = (long)jn * pitch + m.ecol;
       tl_cp8(base + edge_off + 0, r + oe);
@@ -155,7 +155,7 @@ __device__ __forceinline__ void tl_cg_a_item(const CgAParams &P, const CgAIter &
     const double2 c_ky = m.ld_ok ? tl_lds2(base + 2 * 512 + lane_off) : z2;
     const double2 c_kx = m.ld_ok ? tl_lds2(base + 3 * 512 + lane_off) : z2;
     double2 c_u = (upd && m.acta) ? tl_lds2(base + 4 * 512 + lane_off) : z2;
-    if (UM == TL_U_LAZY && upd2 && m.acta) {
+    if (upd2 && upd && m.acta) {
       const double2 c_po = tl_lds2(base + 5 * 512 + lane_off);
       c_u.x = c_u.x + alpha_prev2 * c_po.x;
       c_u.y = c_u.y + alpha_prev2 * c_po.y;
@@ -220,18 +220,19 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_fused_w_ring(cons
   I.it = it;
   I.first = (it == st->cfg.first_it);
   I.beta = 0.0; I.alpha_prev = 0.0;
-  I.upd2 = false; I.alpha_prev2 = 0.0;
+  I.alpha_prev2 = 0.0;
+  if (P.lazy_role) {   // the host alternates the kernels of a lazy loop: this one must sit on an iteration of its parity
+    const int off = it - st->cfg.first_it;
+    if ((off & 1) != (P.lazy_role == 1 ? 1 : 0)) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) st->sched_error = 1;
+      return;
+    }
+  }
   if (!I.first) {
     const double rr_prev = P.hist_rr[it - 1];
     I.beta = rr_cur / rr_prev;
     I.alpha_prev = rr_prev / P.hist_pw[it];
-    if (UM == TL_U_LAZY) {
-      const int off = it - st->cfg.first_it;      // iterations executed so far in this phase
-      if (off >= 2 && tl_cg_lazy_pending(off) == 2) {
-        I.upd2 = true;
-        I.alpha_prev2 = P.hist_rr[it - 2] / P.hist_pw[it - 1];
-      }
-    }
+    if (UM == TL_U_LAZY) I.alpha_prev2 = P.hist_rr[it - 2] / P.hist_pw[it - 1];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_rr[it] = rr_cur;
   double acc[1] = {0.0};
