@@ -19,7 +19,10 @@ CASES = [("cg", 97, 61, {}, {}), ("cg", 130, 40, {}, {"cg_persist": 1}), ("cg", 
          ("jacobi", 50, 45, {"maxiters": 120}, {}), ("cg", 1, 40, {}, {}), ("cg", 200, 3, {"halodepth": 3}, {}),
          # round 2: TMA ring of kernel A, odd PPCG inner count (pairs + trailing step), 5-slot pair ring, Chebyshev pairs
          ("cg", 130, 70, {}, {"a_tma": 4}), ("cg", 63, 40, {}, {"a_tma": 3}), ("ppcg", 97, 61, {"ppcginnersteps": 5}, {}),
-         ("cheby", 130, 70, {}, {"pair_stages": 5}), ("ppcg", 70, 90, {"ppcginnersteps": 6}, {"pair_stages": 5})]
+         ("cheby", 130, 70, {}, {"pair_stages": 5}), ("ppcg", 70, 90, {"ppcginnersteps": 6}, {"pair_stages": 5}),
+         # lazy u update of the CG loop (default on: the cases above run it at ring depth 3, two CTAs per SM): the other flavours
+         ("cg", 97, 61, {}, {"cg_lazy_u": 0}), ("cg", 131, 45, {}, {"cg_lazy_heavy_ctas": 3}), ("cg", 67, 80, {}, {"ring_stages": 4}),
+         ("cg", 65, 33, {"maxiters": 7}, {"ring_stages": 6})]
 
 
 def main():
