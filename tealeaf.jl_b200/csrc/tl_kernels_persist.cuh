@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, MINB) k_cg_persist(const CgP
       int next = 0;
       if (threadIdx.x == 0) next = (int)atomicAdd(qa, 1u);    // in flight while this item streams
       double acc = 0.0;
-      tl_cg_a_item<true, S, true>(P.A, I, item, ring_raw, acc);
+      tl_cg_a_item<TL_U_EVERY, S, true>(P.A, I, item, ring_raw, acc);
       const double t = tl_block_sum(acc, sm);
       if (threadIdx.x == 0) { part_a[item] = t; s_item = next; }
       __syncthreads();

@@ -63,6 +63,7 @@ struct CgAIter {
 #define TL_U_LAZY 2
 #define TL_CGA_FIELDS(UM) ((UM) == TL_U_LAZY ? 6 : (UM) == TL_U_EVERY ? 5 : 4)
 #define TL_CGA_STAGE_BYTES(UM) (TL_CGA_FIELDS(UM) * 512 + 64)
+static_assert(TL_CGA_STAGE_BYTES(TL_U_EVERY) == TL_RING_STAGE_BYTES, "the persistent kernel sizes kernel A's ring with TL_RING_STAGE_BYTES");
 // pending u updates after `off` executed iterations of a lazy phase (off >= 1)
 __host__ __device__ inline int tl_cg_lazy_pending(int off) { return (off & 1) ? 1 : 2; }
 
