@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "tealeaf.jl_b200", "csrc", "libtealeaf_b200.so")
-HOT = ["k_cg_fused_w_ringILi2ELi3ELi3E", "k_cg_fused_w_ringILi2ELi4ELi2E", "k_cg_fused_w_ringILi1ELi3ELi3E", "k_cg_fused_w_tmaILb1ELi4ELi2E", "k_cg_fused_r9CgBParams",
+HOT = ["k_cg_fused_w_ringILi2ELi3ELi2E", "k_cg_fused_w_ringILi0ELi3ELi3E", "k_cg_fused_w_ringILi2ELi4ELi2E", "k_cg_fused_w_ringILi0ELi4ELi2E", "k_cg_fused_w_ringILi1ELi3ELi3E", "k_cg_fused_w_tmaILb1ELi4ELi2E", "k_cg_fused_r9CgBParams",
        "k_cheby_fused_ringILb0ELi3ELi3E", "k_cheby_pair_ringILi4ELi2ELb0E", "k_cheby_pair_ringILi4ELi2ELb1E",
        "k_ppcg_inner_ringILi3ELi3E", "k_ppcg_pair_ringILi4ELi2ELb0E", "k_ppcg_pair_ringILi4ELi2ELb1E", "k_jacobi_fused_ringILi3ELi3E"]
 GROUPS = [("FP64 (DADD/DMUL/DFMA)", r"^(DADD|DMUL|DFMA)$"), ("global/shared data (LDG/STG/LDS/STS/LDGSTS/UTMALDG/UBLKCP)", r"^(LDG|STG|LDS|STS|LDGSTS|UTMALDG|UBLKCP|LDGDEPBAR|DEPBAR)$"),
