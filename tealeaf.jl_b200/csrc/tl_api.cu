@@ -217,6 +217,8 @@ static double *field_ptr(tl_ctx *c, int f) {
   return c->buf[f];
 }
 
+#define TL_STENCIL_CHUNK_ROWS 12
+
 static void make_tiling(const tl_ctx *c, int blocks_per_sm, int chunk_rows, Tiling *tout, int *grid) {
   const Geo &g = c->g;
   Tiling t;
@@ -241,10 +243,11 @@ static void compute_tiling(tl_ctx *c) {
   const long cells_tile = (long)g.nx * g.ny;
   c->ring_eff = c->ring_stages >= 0 ? c->ring_stages : (cells_tile >= (long)8192 * 8192 ? 4 : 3);
   const int bps = (c->ring_eff == 3) ? 3 : (c->ring_eff == 4) ? 2 : 1;   // the kernels' launch bounds
-  // rows per warp: 8 (stencil) / 16 (pointwise) once the mesh fills the machine; small meshes get
-  // shorter chunks so that at least half a wave of warps exists (profiles/r01c_small_mesh_sweep.log)
+  // rows per warp: 12 (stencil) / 16 (pointwise) once the mesh fills the machine (8 until the lazy-u CG loop: with it
+  // whole solves run 2-3 % faster at 11-13 rows at 4096^2 and 2048^2, profiles/r02q_chunk_rows_sweep.log); small meshes
+  // get shorter chunks so that at least half a wave of warps exists (profiles/r01c_small_mesh_sweep.log)
   const long warp_rows = (long)((g.nx + TL_STRIP - 1) / TL_STRIP) * g.ny;
-  int cr = (int)std::min<long>(8, std::max<long>(1, warp_rows / ((long)c->num_sms * bps * 4)));
+  int cr = (int)std::min<long>(TL_STENCIL_CHUNK_ROWS, std::max<long>(1, warp_rows / ((long)c->num_sms * bps * 4)));
   int pcr = (int)std::min<long>(16, std::max<long>(1, warp_rows / ((long)c->num_sms * c->pw_blocks_per_sm * 4)));
   if (pcr >= 4) pcr &= ~3;   // the pointwise kernels are unrolled by 4 rows
   // Mid-size tiles (what a 4096^2 mesh becomes on 4-8 GPUs: 1024^2 ... 2048 x 1024 cells) are only one
@@ -643,6 +646,7 @@ extern "C" int tl_get_option(tl_ctx *c, const char *name, double *value) {
   else if (n == "cg_lazy_u") v = c->cg_lazy_u;
   else if (n == "cg_lazy_heavy_ctas") v = c->lazy_heavy_ctas;
   else if (n == "cg_u_mode") v = cg_u_mode(c);
+  else if (n == "default_chunk_rows") v = TL_STENCIL_CHUNK_ROWS;
   else if (n == "cg_a_blocks_per_sm") {
     int occ = 0;
     CU(c, cudaSetDevice(c->device));

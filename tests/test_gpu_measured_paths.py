@@ -108,13 +108,13 @@ def test_pair_kernels_match_oracle_at_size(solver, n):
 @pytest.mark.timeout(1200)
 def test_ring4_and_grid_clamp_match_oracle_8192():
     """8192^2 selects ring depth 4 at 2 CTAs/SM automatically and the grid bound clamps the number of row
-    chunks (rows_per_chunk > 8): the same code path as the 16384^2 tiles of the weak-scaling runs.  CG capped at
+    chunks (rows_per_chunk above the default of 12): the same code path as the 16384^2 tiles of the weak-scaling runs.  CG capped at
     30 iterations against the OpenMP oracle, element-wise."""
     n, cap = 8192, 30
     s = lambda: classic_settings(n, steps=1, solver="cg", maxiters=cap)
     chunk, geom = tl.initialiseapp(s(), backend=_device())
     assert chunk.get_option("ring_stages_effective") == 4
-    assert chunk.get_option("rows_per_chunk") > 8                      # the clamp bites
+    assert chunk.get_option("rows_per_chunk") > chunk.get_option("default_chunk_rows")     # the clamp bites
     assert chunk.get_option("fused_grid") <= chunk.get_option("max_grid")
     assert chunk.get_option("pw_grid") <= chunk.get_option("max_grid")
     st = s()
@@ -142,7 +142,7 @@ def test_wide_strip_grid_clamp_matches_oracle():
     for solver, over in (("cg", {}), ("ppcg", {"ppcginnersteps": 4, **sw}), ("cheby", sw)):
         s = lambda: classic_settings(nx, ny=ny, steps=1, solver=solver, maxiters=cap, **over)
         chunk, geom = tl.initialiseapp(s(), backend=_device())
-        assert chunk.get_option("rows_per_chunk") > 8 and chunk.get_option("fused_grid") <= chunk.get_option("max_grid")
+        assert chunk.get_option("rows_per_chunk") > chunk.get_option("default_chunk_rows") and chunk.get_option("fused_grid") <= chunk.get_option("max_grid")
         assert chunk.get_option("pair_grid") <= chunk.get_option("max_grid")
         recs, final = tl.diffuse(chunk, s(), geom)
         o, og = tl.initialiseapp(s(), backend=omp_oracle())
@@ -184,7 +184,7 @@ def test_full_size_8192_cg_properties():
     """8192^2 CG to convergence (more than the deck's 10000 iterations: ~1.2 N)."""
     s = classic_settings(8192, steps=1, solver="cg", checkresult=True, maxiters=20000)
     chunk, geom = tl.initialiseapp(s, backend=_device())
-    assert chunk.get_option("ring_stages_effective") == 4 and chunk.get_option("rows_per_chunk") > 8
+    assert chunk.get_option("ring_stages_effective") == 4 and chunk.get_option("rows_per_chunk") > chunk.get_option("default_chunk_rows")
     recs, final = tl.diffuse(chunk, s, geom)
     assert 8000 < recs[0]["iters"] < 14000, recs
     assert np.sqrt(abs(recs[0]["error"])) < 1e-15
