@@ -355,7 +355,7 @@ def run_b200(args):
 
     # N>1: the same tile solved alone on this GPU (no neighbours, no exchange), so that the
     # weak-scaling efficiency of THIS workload can be read from one JSON line
-    solo = None
+    solo = solo_fastest = None
     if world > 1:
         ssolo = classic(tile_nx, tile_ny, 1, maxiters=maxiters)     # the same iteration cap as the N-GPU timestep
         csolo = DeviceChunk(tile_nx, tile_ny, ssolo.halodepth, ssolo.maxiters, device=local_rank)
@@ -375,7 +375,13 @@ def run_b200(args):
             csolo.timer_start()
             isolo = solo_step()
             solo_ms = csolo.timer_stop()
-        solo = tile_nx * tile_ny * isolo["iters"] / (solo_ms * 1e-3)
+        # every rank times its own tile alone; like the N-GPU value, the line reports the SLOWEST GPU of the job
+        t_solo = torch.tensor([solo_ms, solo_ms], dtype=torch.float64, device="cuda")
+        t_fast = t_solo.clone()
+        dist.all_reduce(t_solo, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_fast, op=dist.ReduceOp.MIN)
+        solo = tile_nx * tile_ny * isolo["iters"] / (float(t_solo[0].item()) * 1e-3)
+        solo_fastest = tile_nx * tile_ny * isolo["iters"] / (float(t_fast[0].item()) * 1e-3)
         csolo.close()
     chunk = DeviceChunk(tile_nx, tile_ny, s.halodepth, s.maxiters, device=local_rank, rank=rank, px=px, py=py)
     if world > 1:
@@ -555,8 +561,8 @@ def run_b200(args):
                     "host_numa_binding": numa},
             "gpu_launches": int(launches), "clocks": clocks,
             **({"other_configs": other} if other else {}),
-            **({"same_tile_single_gpu": {"value": solo, "unit": UNIT, "note":
-                "this rank's tile solved alone (1x1, one timestep exactly as timed at N GPUs: same iteration cap) in the same job; "
+            **({"same_tile_single_gpu": {"value": solo, "fastest_gpu_value": solo_fastest, "unit": UNIT, "note":
+                "every rank's tile solved alone (1x1, one timestep exactly as timed at N GPUs: same iteration cap) in the same job, value = the slowest GPU's (as the N-GPU value is a max over ranks), fastest_gpu_value = the fastest one's; "
                 "weak-scaling efficiency of the N-GPU workload = value / (N x this)"}} if solo else {}),
         }))
     if dist is not None:
