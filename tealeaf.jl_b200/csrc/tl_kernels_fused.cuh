@@ -126,6 +126,20 @@ __device__ __forceinline__ void tl_reflect_edges(double *f, const Geo &g, const 
 // HBM traffic per cell: read r, p, u, kx, ky; write p, u, w  = 64 B (48 B without u; TL_U_LAZY, the default of the CG
 // loop, touches u every second launch only: 72 / 48 B, see tl_kernels_ring.cuh).
 // ------------------------------------------------------------------------------------------
+// How a launch of kernel A advances u (template parameter UM):
+//   TL_U_NONE   not at all (PPCG outer: k_ppcg_ur_sd does it; the odd iterations of a lazy CG loop)        48 B per cell
+//   TL_U_EVERY  u += alpha(it-1) p(it-1)                                                                    64 B
+//   TL_U_LAZY   u = (u + alpha(it-2) p(it-2)) + alpha(it-1) p(it-1): p(it-2) still sits in the ping-pong
+//               buffer this launch is about to overwrite, so it costs one more read of 8 B                  72 B
+// A lazy CG loop (option cg_lazy_u) launches TL_U_LAZY on the even iterations of the phase and TL_U_NONE on the odd
+// ones: 60 B on average.  Same operations in the same order as an update per iteration (CG.jl:95), hence the same bits.
+// The host alternates the two kernels (chunks of an even number of iterations), each checks the parity it was given.
+#define TL_U_NONE 0
+#define TL_U_EVERY 1
+#define TL_U_LAZY 2
+// pending u updates after `off` executed iterations of a lazy phase (off >= 1): what k_cg_flush has to apply
+__host__ __device__ inline int tl_cg_lazy_pending(int off) { return (off & 1) ? 1 : 2; }
+
 struct CgAParams {
   Geo g; Tiling t;
   SolveState *st;
@@ -226,7 +240,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_fused_r(const CgBPar
 // (u += alpha p ; p = beta p + r) including the depth-1 halo write-through, so that memory
 // holds the reference's post-iteration state.  Pointwise.
 // ------------------------------------------------------------------------------------------
-// UM: how the loop's kernel A advanced u (TL_U_NONE / TL_U_EVERY / TL_U_LAZY, tl_kernels_ring.cuh -- 0 / 1 / 2);
+// UM: how the loop's kernel A advanced u (TL_U_NONE / TL_U_EVERY / TL_U_LAZY);
 // after a TL_U_LAZY loop one or two updates are pending, the older p still sits in the other ping-pong buffer.
 template <int UM>
 __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_flush(const CgAParams P) {
@@ -235,7 +249,7 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_flush(const CgAParam
   if (it == st->cfg.first_it) return;
   const double rr_cur = st->red_rr, rr_prev = P.hist_rr[it - 1];
   const double beta = rr_cur / rr_prev, alpha = rr_prev / P.hist_pw[it];
-  const bool two = (UM == 2) && ((it - st->cfg.first_it) & 1) == 0;
+  const bool two = (UM == TL_U_LAZY) && tl_cg_lazy_pending(it - st->cfg.first_it) == 2;
   const double alpha2 = two ? P.hist_rr[it - 2] / P.hist_pw[it - 1] : 0.0;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.hist_rr[it] = rr_cur;
   // pointwise, so done IN PLACE in the buffer kernel A of iteration `it` wrote: the current p
@@ -258,16 +272,16 @@ __global__ void __launch_bounds__(TL_FUSED_THREADS, 4) k_cg_flush(const CgAParam
       const double pn = beta * pv + P.r[o];
       pout[o] = pn;
       double un = 0.0;
-      if (UM != 0) {
+      if (UM != TL_U_NONE) {
         un = P.u[o];
         if (two) un = un + alpha2 * pold[o];
         un = un + alpha * pv;
         P.u[o] = un;
       }
-      if (physL && i == 0) { pout[o - 1] = pn; if (UM != 0) P.u[o - 1] = un; }
-      if (physR && i == g.nx - 1) { pout[o + 1] = pn; if (UM != 0) P.u[o + 1] = un; }
-      if (physB && j == 0) { pout[o - g.pitch] = pn; if (UM != 0) P.u[o - g.pitch] = un; }
-      if (physT && j == g.ny - 1) { pout[o + g.pitch] = pn; if (UM != 0) P.u[o + g.pitch] = un; }
+      if (physL && i == 0) { pout[o - 1] = pn; if (UM != TL_U_NONE) P.u[o - 1] = un; }
+      if (physR && i == g.nx - 1) { pout[o + 1] = pn; if (UM != TL_U_NONE) P.u[o + 1] = un; }
+      if (physB && j == 0) { pout[o - g.pitch] = pn; if (UM != TL_U_NONE) P.u[o - g.pitch] = un; }
+      if (physT && j == g.ny - 1) { pout[o + g.pitch] = pn; if (UM != TL_U_NONE) P.u[o + g.pitch] = un; }
     }
   }
 }

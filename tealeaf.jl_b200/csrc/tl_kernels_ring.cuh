@@ -50,22 +50,10 @@ struct CgAIter {
   double alpha_prev2;   // TL_U_LAZY: alpha of iteration it-2
 };
 
-// How a launch of kernel A advances u (template parameter UM):
-//   TL_U_NONE   not at all (PPCG outer: k_ppcg_ur_sd does it; the odd iterations of a lazy CG loop)        48 B per cell
-//   TL_U_EVERY  u += alpha(it-1) p(it-1)                                                                    64 B
-//   TL_U_LAZY   u = (u + alpha(it-2) p(it-2)) + alpha(it-1) p(it-1): p(it-2) still sits in the ping-pong
-//               buffer this launch is about to overwrite, so it costs one more read of 8 B                  72 B
-// A lazy CG loop (option cg_lazy_u) launches TL_U_LAZY on the even iterations of the phase and TL_U_NONE on the odd
-// ones: 60 B on average.  Same operations in the same order as an update per iteration (CG.jl:95), hence the same bits.
-// The host alternates the two kernels (chunks of an even number of iterations), each checks the parity it was given.
-#define TL_U_NONE 0
-#define TL_U_EVERY 1
-#define TL_U_LAZY 2
+// Ring slot of kernel A: 4 / 5 / 6 fields of 512 B per row, by the way the launch advances u (TL_U_*, tl_kernels_fused.cuh)
 #define TL_CGA_FIELDS(UM) ((UM) == TL_U_LAZY ? 6 : (UM) == TL_U_EVERY ? 5 : 4)
 #define TL_CGA_STAGE_BYTES(UM) (TL_CGA_FIELDS(UM) * 512 + 64)
 static_assert(TL_CGA_STAGE_BYTES(TL_U_EVERY) == TL_RING_STAGE_BYTES, "the persistent kernel sizes kernel A's ring with TL_RING_STAGE_BYTES");
-// pending u updates after `off` executed iterations of a lazy phase (off >= 1)
-__host__ __device__ inline int tl_cg_lazy_pending(int off) { return (off & 1) ? 1 : 2; }
 
 // The rows of one work item (8 warp tasks) of kernel A.  COH = true (persistent kernel: r, p, u change
 // inside the launch) keeps the prologue loads coherent; the ring loads are cp.async (L2) either way.
