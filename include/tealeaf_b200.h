@@ -98,7 +98,9 @@ int tl_abi_version(void);
  * (tests/test_gpu_parity.py states what stays bit-identical).  Defaults are
  * the measured best.  The environment variable TEALEAF_B200_OPTS
  * ("name=value,name=value") applies options to every context the process creates.
- *   chunk_rows, pw_chunk_rows   rows per warp task of the stencil / pointwise kernels (-1 = auto)
+ *   chunk_rows, pw_chunk_rows   rows per warp task of the stencil / pointwise kernels (-1 = auto: default_chunk_rows = 12 / 16 on
+ *                               meshes that fill the machine)
+ *   blocks_per_sm, pw_blocks_per_sm   CTAs per SM the tilings of small meshes are sized for (2 / 4)
  *   ring_stages                 cp.async ring depth of the stencil kernels: -1 auto, 3, 4, 6
  *   graph_iters, use_graph      iterations per CUDA graph launch (8) / plain launches instead
  *   b_reverse                   kernel B walks the tile top-down (1)
@@ -130,7 +132,7 @@ int tl_abi_version(void);
 int tl_set_option(tl_ctx *ctx, const char *name, double value);
 /* Read-back of any option above, and of derived quantities: ring_stages_effective (the ring depth in use),
  * rows_per_chunk / pw_rows_per_chunk / pair_rows_per_chunk and fused_grid / pw_grid / pair_grid (how the tile
- * is cut into warp tasks and CTAs), max_grid (the bound on a grid: the partials array), num_sms, cg_u_mode (1: u advanced every
+ * is cut into warp tasks and CTAs), max_grid (the bound on a grid: the partials array), num_sms, default_chunk_rows, cg_u_mode (1: u advanced every
  * iteration, 2: every second one -- what cg_lazy_u resolves to), cg_a_blocks_per_sm (resident CTAs of kernel A), last_cg_phase_ms
  * (device time of the CG phase -- preamble, CG presteps, flush -- of the last Chebyshev / PPCG solve), prof_* (above).
  * On a tl_create_multi context: the maximum over the tiles. */

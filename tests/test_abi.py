@@ -55,3 +55,21 @@ def test_product_path_never_imports_the_oracle():
                     not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
                 assert "liboracle" not in src and "tlo_" not in src, f
+
+
+def test_every_option_is_documented_in_the_header_and_readable():
+    """tl_set_option / tl_get_option names (csrc/tl_api.cu) vs the option list in include/tealeaf_b200.h: every knob is
+    documented, and every knob that can be set can be read back (the tests assert code paths through the read-back)."""
+    import re
+    src = open(os.path.join(ROOT, "tealeaf.jl_b200", "csrc", "tl_api.cu")).read()
+    hdr = open(os.path.join(ROOT, "include", "tealeaf_b200.h")).read()
+    i, j = src.index('extern "C" int tl_set_option'), src.index('extern "C" int tl_get_option')
+    set_names = set(re.findall(r'n == "([a-z0-9_]+)"', src[i:j]))
+    get_names = set(re.findall(r'n == "([a-z0-9_]+)"', src[j:src.index('extern "C"', j + 10)]))
+    doc = hdr[hdr.index("Tuning / A-B knobs"):hdr.index("int tl_get_option")]
+    documented = set(re.findall(r"\b([a-z][a-z0-9_]{3,})\b", doc))
+    assert len(set_names) > 25 and len(get_names) > len(set_names)
+    assert not set_names - documented, sorted(set_names - documented)
+    undocumented = {n for n in get_names - documented if not n.startswith(("prof_", "debug_"))}
+    assert not undocumented, sorted(undocumented)
+    assert not set_names - get_names, sorted(set_names - get_names)
