@@ -35,3 +35,30 @@ def test_reference_arm_other_ranks_do_nothing():
     r = run_arm({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29999"}, "--gpus", "2")
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip() == ""
+
+
+def test_recorded_bench_lines_carry_the_contract_keys():
+    """The B200 arm's lines recorded at HEAD (profiles/r02q_bench_n{1,2,4}_*.json, written by bench.py on the GPU boxes):
+    every key the measurement contract names is there and self-consistent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02q_bench_n[124]_*.json")))
+    assert len(files) >= 3, files
+    for f in files:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+            assert k in d, (f, k)
+        assert d["metric"] == "solver cell-iterations/sec" and d["dtype"] == "f64" and d["scaling"] == "weak" and d["warmup"] >= 3
+        assert "workload" in d["config"] and "model" not in d["config"]
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert r["traffic"] is None or r["traffic"] > 0
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] <= 1.02 * d["value"]
+        assert d["gpu_launches"] > 0
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+        assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+        if d["n_gpus"] == 1:
+            assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+            assert "weak_tile_16384" in d["other_configs"] and "chebyshev_4096" in d["other_configs"] and "ppcg_8192" in d["other_configs"]
+        else:
+            assert "same_tile_single_gpu" in d and "chebyshev_4096" in d["other_configs"] and "ppcg_8192" in d["other_configs"]
